@@ -1,0 +1,793 @@
+// render.cu -- fused per-ray volumetric render for SANeRF-HQ (sm_100a).
+//
+// One persistent launch replaces the ~250 ATen + encoder launches of the reference's
+// `NeRFRenderer.run` (nerf/renderer.py:221-385, eval mode, perturb=False) for ALL rays of a frame
+// (the reference additionally loops over max_ray_batch chunks, renderer.py:195-217).
+//
+// Mapping: one warp per ray, lanes = samples.  The three sampling stages (128 / 64 / 32 samples,
+// main.py:84-85) run back to back inside the warp:
+//   stage 0,1  positions from the current bins -> L-inf contraction -> proposal hash grid
+//              (L<=5 levels, C=2) -> 2L->16->1 MLP -> sigma -> weights (warp scan) -> sample_pdf
+//              (warp scan for the cdf, per-lane binary search in shared memory)
+//   stage 2    hash grid (L<=16, C=2) -> 2L->Hg->Hg->16 MLP -> sigma, geo_feat -> weights ->
+//              alpha compositing by warp reductions -> deferred view MLP (31->Hv->Hv->3, one
+//              hidden unit per lane) -> sigmoid + background.
+// Optional heads gather the C=8 feature grid (s_grid / m_grid) per sample in the same pass.
+// Nothing per-sample ever goes to HBM except the optional parity taps.
+//
+// Shared memory: all MLP weights staged once per CTA (persistent CTAs, one per SM) + 2 KB of
+// per-warp scratch (bins ping-pong, delta*sigma / weights, cdf).  Hash tables are read through
+// L1/L2 (54 MiB of RGB tables are L2-resident on B200's 126 MB L2).
+//
+// Arithmetic follows the reference op by op (unfused mul/add where torch rounds twice, IEEE
+// division, expf), see the comments citing renderer.py lines; reductions use a different
+// association than ATen's (warp tree), which is within fp32 summation-order noise.
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace sanerf {
+
+constexpr int kWarps = 16;              // warps (= rays in flight) per CTA
+constexpr int kThreads = kWarps * 32;
+constexpr int kMaxT = 128;              // samples of the widest stage
+constexpr unsigned kFull = 0xffffffffu;
+
+// ---- device-side model description (kernel parameter, constant bank) -------------------------
+struct GridDev {
+    const float* emb;
+    uint32_t L, C;
+    uint32_t off[SANERF_MAX_LEVELS];    // row offset of the level
+    uint32_t res[SANERF_MAX_LEVELS];    // kernel-side resolution
+    uint32_t hmask[SANERF_MAX_LEVELS];  // rows-1 for hashed levels (rows is a power of two), 0 = dense
+};
+
+struct RenderParams {
+    GridDev prop[2], grid, sgrid, mgrid;
+    const float* prop_w0[2];
+    const float* prop_w1[2];
+    const float* grid_w[3];
+    const float* view_w[3];
+    float aabb[6];
+    float min_near, bound;
+    uint32_t contract, last_opaque;
+    const float* u65;
+    const float* u33;
+    // per call
+    const float* rays_o;
+    const float* rays_d;
+    uint32_t N;
+    const float* cnf;
+    uint32_t cnf_rows;
+    const float* bg;
+    uint32_t bg_rows;
+    float bg_scalar;
+    float* image;
+    float* depth;
+    float* wsum;
+    float* sam_in;
+    float* mask_in;
+    int16_t* inds0;
+    int16_t* inds1;
+    float* weights2;
+    float* sigma2;
+    float* bins2;
+    float* f_image;
+};
+
+// ---- small helpers ------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFull, v, o);
+    return v;
+}
+
+__device__ __forceinline__ float warp_inclusive_scan(float v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const float n = __shfl_up_sync(kFull, v, o);
+        if (lane >= o) v += n;
+    }
+    return v;
+}
+
+// torch.nan_to_num(x, nan=0): NaN -> 0, +-inf -> +-FLT_MAX
+__device__ __forceinline__ float nan_to_num0(float x) {
+    if (isnan(x)) return 0.0f;
+    if (isinf(x)) return x > 0 ? CUDART_MAX_NORMAL_F : -CUDART_MAX_NORMAL_F;
+    return x;
+}
+
+// spacing_fn / spacing_fn_inv (renderer.py:249-252)
+__device__ __forceinline__ float spacing(float x) { return x < 1.0f ? x * 0.5f : __fsub_rn(1.0f, __fdiv_rn(1.0f, 2.0f * x)); }
+__device__ __forceinline__ float spacing_inv(float x) { return x < 0.5f ? 2.0f * x : __fdiv_rn(1.0f, __fsub_rn(2.0f, 2.0f * x)); }
+
+// real_bins = spacing_fn_inv(s_near * (1 - bins) + s_far * bins)   (renderer.py:277), unfused like torch
+__device__ __forceinline__ float real_bin(float b, float s_near, float s_far) {
+    return spacing_inv(__fadd_rn(__fmul_rn(s_near, __fsub_rn(1.0f, b)), __fmul_rn(s_far, b)));
+}
+
+// L-inf contraction (renderer.py:60-69)
+__device__ __forceinline__ void contract3(float& x, float& y, float& z) {
+    const float ax = fabsf(x), ay = fabsf(y), az = fabsf(z);
+    float mag = ax;
+    int idx = 0;
+    if (ay > mag) { mag = ay; idx = 1; }
+    if (az > mag) { mag = az; idx = 2; }
+    if (mag < 1.0f) return;
+    const float inv = __fdiv_rn(1.0f, mag);
+    const float big = __fdiv_rn(__fsub_rn(2.0f, inv), mag);
+    x = __fmul_rn(x, idx == 0 ? big : inv);
+    y = __fmul_rn(y, idx == 1 ? big : inv);
+    z = __fmul_rn(z, idx == 2 ? big : inv);
+}
+
+// One level of a C-channel grid at a point in [0,1]^3: same arithmetic as grid_encode.cu / the
+// reference kernel (gridencoder.cu:140-195) with the per-level constants taken from GridDev.
+template <int C>
+__device__ __forceinline__ void encode_level(const GridDev& g, int l, const float (&x)[3], float (&out)[C]) {
+    const uint32_t res = g.res[l];
+    const uint32_t hmask = g.hmask[l];
+    const float* __restrict__ rows = g.emb + (size_t)g.off[l] * C;
+    const float resf = (float)res, top = (float)(res - 1);
+    uint32_t b0[3], b1[3];
+    float f[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        float pos = fminf(fmaxf(__fmaf_rn(x[d], resf, -0.5f), 0.0f), top);
+        const float fl = floorf(pos);
+        b0[d] = (uint32_t)fl;
+        b1[d] = min(b0[d] + 1, res - 1);
+        f[d] = pos - fl;
+    }
+    uint32_t row[8];
+    float w[8];
+    if (hmask == 0) {  // dense level: x + y*res + z*res^2 < rows, no modulo needed
+        const uint32_t y0 = b0[1] * res, y1 = b1[1] * res, z0 = b0[2] * res * res, z1 = b1[2] * res * res;
+#pragma unroll
+        for (int i = 0; i < 8; i++) row[i] = ((i & 1) ? b1[0] : b0[0]) + ((i & 2) ? y1 : y0) + ((i & 4) ? z1 : z0);
+    } else {
+        const uint32_t y0 = b0[1] * 2654435761u, y1 = b1[1] * 2654435761u, z0 = b0[2] * 805459861u, z1 = b1[2] * 805459861u;
+#pragma unroll
+        for (int i = 0; i < 8; i++) row[i] = (((i & 1) ? b1[0] : b0[0]) ^ ((i & 2) ? y1 : y0) ^ ((i & 4) ? z1 : z0)) & hmask;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float ww = (i & 1) ? f[0] : 1 - f[0];
+        ww *= (i & 2) ? f[1] : 1 - f[1];
+        ww *= (i & 4) ? f[2] : 1 - f[2];
+        w[i] = ww;
+    }
+    if constexpr (C == 2) {
+        float2 v[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __ldg(reinterpret_cast<const float2*>(rows) + row[i]);
+        out[0] = 0.f; out[1] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            out[0] = __fmaf_rn(w[i], v[i].x, out[0]);
+            out[1] = __fmaf_rn(w[i], v[i].y, out[1]);
+        }
+    } else {
+        static_assert(C == 8, "feature grids use 8 channels");
+        float4 va[8], vb[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const float4* p = reinterpret_cast<const float4*>(rows) + (size_t)row[i] * 2;
+            va[i] = __ldg(p);
+            vb[i] = __ldg(p + 1);
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) out[c] = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            out[0] = __fmaf_rn(w[i], va[i].x, out[0]); out[1] = __fmaf_rn(w[i], va[i].y, out[1]);
+            out[2] = __fmaf_rn(w[i], va[i].z, out[2]); out[3] = __fmaf_rn(w[i], va[i].w, out[3]);
+            out[4] = __fmaf_rn(w[i], vb[i].x, out[4]); out[5] = __fmaf_rn(w[i], vb[i].y, out[5]);
+            out[6] = __fmaf_rn(w[i], vb[i].z, out[6]); out[7] = __fmaf_rn(w[i], vb[i].w, out[7]);
+        }
+    }
+}
+
+// y[n] = sum_k W[n][k] x[k], W in shared memory as [N][KP] (KP = K rounded up to 4, zero padded);
+// every lane reads the same address (broadcast LDS.128), activations stay in registers.
+template <int K, int KP, int N, bool RELU>
+__device__ __forceinline__ void dense(const float* __restrict__ W, const float (&x)[K], float (&y)[N]) {
+#pragma unroll
+    for (int n = 0; n < N; n++) {
+        float acc = 0.f;
+#pragma unroll
+        for (int k = 0; k < KP; k += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(W + n * KP + k);
+            acc = __fmaf_rn(w.x, x[k], acc);
+            if (k + 1 < K) acc = __fmaf_rn(w.y, x[k + 1], acc);
+            if (k + 2 < K) acc = __fmaf_rn(w.z, x[k + 2], acc);
+            if (k + 3 < K) acc = __fmaf_rn(w.w, x[k + 3], acc);
+        }
+        y[n] = RELU ? fmaxf(acc, 0.f) : acc;
+    }
+}
+
+// ---- shared memory plan ---------------------------------------------------------------------
+template <int PL, int GL, int HG>
+struct Smem {
+    static constexpr int PK = 2 * PL, PKP = (PK + 3) & ~3;  // proposal MLP input width (padded)
+    static constexpr int GK = 2 * GL;                        // grid MLP input width (multiple of 4 for GL even)
+    static constexpr int VP = 33;                            // view MLP row pitch (bank-conflict free)
+    // offsets in floats
+    static constexpr int prop_w0 = 0;                        // [2][16][PKP]
+    static constexpr int prop_w1 = prop_w0 + 2 * 16 * PKP;   // [2][16]
+    static constexpr int grid_w0 = prop_w1 + 2 * 16;         // [HG][GK]
+    static constexpr int grid_w1 = grid_w0 + HG * GK;        // [HG][HG]
+    static constexpr int grid_w2 = grid_w1 + HG * HG;        // [16][HG]
+    static constexpr int view_w0 = grid_w2 + 16 * HG;        // [32][VP]  (rows >= Hv zero)
+    static constexpr int view_w1 = view_w0 + 32 * VP;        // [32][VP]
+    static constexpr int view_w2 = view_w1 + 32 * VP;        // [3][32]
+    static constexpr int utab = view_w2 + 3 * 32;            // u65 (68 slots) + u33 (36 slots)
+    static constexpr int scratch = (utab + 68 + 36 + 3) & ~3;
+    // per-warp scratch
+    static constexpr int s_bins = 0;      // [2][132]
+    static constexpr int s_ds = 264;      // [128]
+    static constexpr int s_cdf = 392;     // [132]
+    static constexpr int per_warp = 524;
+    static constexpr int total = scratch + kWarps * per_warp;
+    static_assert(GK % 4 == 0 && HG % 16 == 0, "grid MLP widths");
+};
+
+template <int PL, int GL, int HG, int HV>
+__device__ void stage_weights(float* sm, const RenderParams& p) {
+    using S = Smem<PL, GL, HG>;
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 2 * 16 * S::PKP; i += kThreads) {
+        const int e = i / (16 * S::PKP), r = (i / S::PKP) % 16, k = i % S::PKP;
+        sm[S::prop_w0 + i] = k < S::PK ? __ldg(p.prop_w0[e] + r * S::PK + k) : 0.f;
+    }
+    for (int i = tid; i < 32; i += kThreads) sm[S::prop_w1 + i] = __ldg(p.prop_w1[i / 16] + (i % 16));
+    for (int i = tid; i < HG * S::GK; i += kThreads) sm[S::grid_w0 + i] = __ldg(p.grid_w[0] + i);
+    for (int i = tid; i < HG * HG; i += kThreads) sm[S::grid_w1 + i] = __ldg(p.grid_w[1] + i);
+    for (int i = tid; i < 16 * HG; i += kThreads) sm[S::grid_w2 + i] = __ldg(p.grid_w[2] + i);
+    for (int i = tid; i < 32 * S::VP; i += kThreads) {
+        const int n = i / S::VP, k = i % S::VP;
+        sm[S::view_w0 + i] = (n < HV && k < 31) ? __ldg(p.view_w[0] + n * 31 + k) : 0.f;
+        sm[S::view_w1 + i] = (n < HV && k < HV) ? __ldg(p.view_w[1] + n * HV + k) : 0.f;
+    }
+    for (int i = tid; i < 3 * 32; i += kThreads) {
+        const int c = i / 32, k = i % 32;
+        sm[S::view_w2 + i] = k < HV ? __ldg(p.view_w[2] + c * HV + k) : 0.f;
+    }
+    for (int i = tid; i < 65; i += kThreads) sm[S::utab + i] = __ldg(p.u65 + i);
+    for (int i = tid; i < 33; i += kThreads) sm[S::utab + 68 + i] = __ldg(p.u33 + i);
+}
+
+// weights of one stage from delta*sigma (renderer.py:308-325); ds[] (shared, per warp) is
+// overwritten with the weights.  T samples, sample j = lane + 32*i.
+template <int T>
+__device__ __forceinline__ void weights_from_ds(float* ds, int lane, bool last_opaque) {
+    float carry = 0.f;
+#pragma unroll
+    for (int i = 0; i < T / 32; i++) {
+        const int j = lane + 32 * i;
+        const float v = ds[j];
+        const float incl = warp_inclusive_scan(v, lane);
+        float excl = __shfl_up_sync(kFull, incl, 1);
+        if (lane == 0) excl = 0.f;
+        excl += carry;                         // sum of delta*sigma over samples before j
+        carry += __shfl_sync(kFull, incl, 31);
+        const float vv = (last_opaque && j == T - 1) ? CUDART_INF_F : v;
+        const float alpha = 1.0f - expf(-vv);
+        const float tr = expf(-excl);
+        ds[j] = nan_to_num0(alpha * tr);
+    }
+}
+
+// sample_pdf (renderer.py:84-119), perturb=False.  w[] = T0 weights, bins[] = T0+1 bins (shared);
+// writes TN new bins; cdf[] is scratch (T0+1).  u = linspace(.5/TN, 1-.5/TN, TN) table (shared).
+template <int T0, int TN>
+__device__ __forceinline__ void sample_pdf_warp(const float* w, const float* bins, float* cdf, const float* u, float* out, int lane,
+                                                int16_t* inds_out) {
+    constexpr int PER = T0 / 32;
+    float wp[PER];
+    float part = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        wp[i] = w[lane + 32 * i] + 0.01f;
+        part += wp[i];
+    }
+    const float total = warp_sum(part);
+    float carry = 0.f;
+    if (lane == 0) cdf[0] = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER; i++) {
+        const float pdf = __fdiv_rn(wp[i], total);
+        const float incl = warp_inclusive_scan(pdf, lane) + carry;
+        carry = __shfl_sync(kFull, incl, 31);
+        cdf[lane + 32 * i + 1] = fminf(incl, 1.0f);
+    }
+    __syncwarp();
+    for (int k = lane; k < TN; k += 32) {
+        const float uk = u[k];
+        int lo = 0, hi = T0 + 1;               // searchsorted(cdf, u, right=True): #entries <= u
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (cdf[mid] <= uk) lo = mid + 1; else hi = mid;
+        }
+        const int below = min(max(lo - 1, 0), T0), above = min(lo, T0);
+        const float c0 = cdf[below], c1 = cdf[above], g0 = bins[below], g1 = bins[above];
+        float t = nan_to_num0(__fdiv_rn(__fsub_rn(uk, c0), __fsub_rn(c1, c0)));
+        t = fminf(fmaxf(t, 0.f), 1.f);
+        out[k] = __fadd_rn(g0, __fmul_rn(t, __fsub_rn(g1, g0)));
+        if (inds_out) inds_out[k] = (int16_t)lo;
+    }
+    __syncwarp();
+}
+
+// degree-4 real SH (shencoder.cu:49-68)
+__device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {
+    const float xy = x * y, xz = x * z, yz = y * z, x2 = x * x, y2 = y * y, z2 = z * z;
+    o[0] = 0.28209479177387814f;
+    o[1] = -0.48860251190291987f * y;
+    o[2] = 0.48860251190291987f * z;
+    o[3] = -0.48860251190291987f * x;
+    o[4] = 1.0925484305920792f * xy;
+    o[5] = -1.0925484305920792f * yz;
+    o[6] = 0.94617469575755997f * z2 - 0.31539156525251999f;
+    o[7] = -1.0925484305920792f * xz;
+    o[8] = 0.54627421529603959f * x2 - 0.54627421529603959f * y2;
+    o[9] = 0.59004358992664352f * y * (-3.0f * x2 + y2);
+    o[10] = 2.8906114426405538f * xy * z;
+    o[11] = 0.45704579946446572f * y * (1.0f - 5.0f * z2);
+    o[12] = 0.3731763325901154f * z * (5.0f * z2 - 3.0f);
+    o[13] = 0.45704579946446572f * x * (1.0f - 5.0f * z2);
+    o[14] = 1.4453057213202769f * z * (x2 - y2);
+    o[15] = 0.59004358992664352f * x * (-x2 + 3.0f * y2);
+}
+
+// sample position for bins (b0,b1): midpoint t, delta, contracted point mapped to [0,1]^3
+struct RayCtx {
+    float ox, oy, oz, dx, dy, dz, s_near, s_far, bound;
+    bool contract;
+};
+
+__device__ __forceinline__ bool sample_point(const RayCtx& r, float b0, float b1, float& tmid, float& delta, float (&x01)[3]) {
+    const float rb0 = real_bin(b0, r.s_near, r.s_far), rb1 = real_bin(b1, r.s_near, r.s_far);
+    tmid = __fadd_rn(rb1, rb0) * 0.5f;                      // renderer.py:279
+    delta = __fsub_rn(rb1, rb0);                            // renderer.py:309
+    float x = __fadd_rn(r.ox, __fmul_rn(r.dx, tmid));       // renderer.py:281-282
+    float y = __fadd_rn(r.oy, __fmul_rn(r.dy, tmid));
+    float z = __fadd_rn(r.oz, __fmul_rn(r.dz, tmid));
+    if (r.contract) contract3(x, y, z);
+    const float den = 2.0f * r.bound;                       // grid.py:156
+    x01[0] = __fdiv_rn(__fadd_rn(x, r.bound), den);
+    x01[1] = __fdiv_rn(__fadd_rn(y, r.bound), den);
+    x01[2] = __fdiv_rn(__fadd_rn(z, r.bound), den);
+    bool oob = false;                                       // gridencoder.cu:105-111 -> zeros
+#pragma unroll
+    for (int d = 0; d < 3; d++) oob |= (x01[d] < 0.f || x01[d] > 1.f);
+    return !oob;
+}
+
+// proposal stage: T samples through proposal network e; fills ds[] with delta*sigma
+template <int T, int PL, int GL, int HG>
+__device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, const float* sm, const RayCtx& r, const float* bins, float* ds,
+                                               int lane) {
+    using S = Smem<PL, GL, HG>;
+    const GridDev& g = p.prop[e];
+    const float* w0 = sm + S::prop_w0 + e * 16 * S::PKP;
+    const float* w1 = sm + S::prop_w1 + e * 16;
+#pragma unroll 1
+    for (int i = 0; i < T / 32; i++) {
+        const int j = lane + 32 * i;
+        float tmid, delta, x01[3];
+        const bool inside = sample_point(r, bins[j], bins[j + 1], tmid, delta, x01);
+        float feat[2 * PL];
+        if (inside) {
+#pragma unroll
+            for (int l = 0; l < PL; l++) {
+                float o[2];
+                encode_level<2>(g, l, x01, o);
+                feat[2 * l] = o[0];
+                feat[2 * l + 1] = o[1];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 2 * PL; k++) feat[k] = 0.f;
+        }
+        float h[16];
+        dense<2 * PL, S::PKP, 16, true>(w0, feat, h);
+        float o = 0.f;
+#pragma unroll
+        for (int k = 0; k < 16; k += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(w1 + k);
+            o = __fmaf_rn(w.x, h[k], o); o = __fmaf_rn(w.y, h[k + 1], o);
+            o = __fmaf_rn(w.z, h[k + 2], o); o = __fmaf_rn(w.w, h[k + 3], o);
+        }
+        ds[j] = __fmul_rn(delta, expf(o));                  // trunc_exp fwd (activation.py:10); renderer.py:310
+    }
+    __syncwarp();
+}
+
+template <int PL, int GL, int HG, int HV, bool SAM, bool MASK>
+__global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_constant__ RenderParams p) {
+    using S = Smem<PL, GL, HG>;
+    extern __shared__ __align__(16) float sm[];
+    stage_weights<PL, GL, HG, HV>(sm, p);
+    __syncthreads();
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* scratch = sm + S::scratch + warp * S::per_warp;
+    float* binsA = scratch + S::s_bins;
+    float* binsB = binsA + 132;
+    float* ds = scratch + S::s_ds;
+    float* cdf = scratch + S::s_cdf;
+    const float* u65 = sm + S::utab;
+    const float* u33 = sm + S::utab + 68;
+    const bool last_opaque = p.last_opaque != 0;
+
+    const uint32_t total_warps = gridDim.x * kWarps;
+    for (uint32_t ray = blockIdx.x * kWarps + warp; ray < p.N; ray += total_warps) {
+        // ---- ray setup: near/far from the AABB (renderer.py:122-139, 231-235) -------------------
+        RayCtx r;
+        r.ox = __ldg(p.rays_o + 3 * (size_t)ray); r.oy = __ldg(p.rays_o + 3 * (size_t)ray + 1); r.oz = __ldg(p.rays_o + 3 * (size_t)ray + 2);
+        r.dx = __ldg(p.rays_d + 3 * (size_t)ray); r.dy = __ldg(p.rays_d + 3 * (size_t)ray + 1); r.dz = __ldg(p.rays_d + 3 * (size_t)ray + 2);
+        r.bound = p.bound;
+        r.contract = p.contract != 0;
+        float near = -CUDART_INF_F, far = CUDART_INF_F;
+        {
+            const float o[3] = {r.ox, r.oy, r.oz}, d[3] = {r.dx, r.dy, r.dz};
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+                const float den = __fadd_rn(d[a], 1e-15f);
+                const float tmin = __fdiv_rn(__fsub_rn(p.aabb[a], o[a]), den);
+                const float tmax = __fdiv_rn(__fsub_rn(p.aabb[a + 3], o[a]), den);
+                near = fmaxf(near, tmin < tmax ? tmin : tmax);
+                far = fminf(far, tmin > tmax ? tmin : tmax);
+            }
+        }
+        if (far < near) { near = 1e9f; far = 1e9f; }
+        near = fmaxf(near, p.min_near);
+        if (p.cnf) {
+            const float* c = p.cnf + (p.cnf_rows > 1 ? 2 * (size_t)ray : 0);
+            near = fmaxf(near, __ldg(c));
+            far = fminf(far, __ldg(c + 1));
+        }
+        r.s_near = spacing(near);
+        r.s_far = spacing(far);
+
+        // ---- stage 0: uniform bins linspace(0,1,129) (renderer.py:262-266; i/128 is exact) ------
+        for (int j = lane; j <= kMaxT; j += 32) binsA[j] = (float)j * (1.0f / kMaxT);
+        __syncwarp();
+        proposal_stage<128, PL, GL, HG>(p, 0, sm, r, binsA, ds, lane);
+        weights_from_ds<128>(ds, lane, last_opaque);
+        __syncwarp();
+        sample_pdf_warp<128, 65>(ds, binsA, cdf, u65, binsB, lane, p.inds0 ? p.inds0 + 65 * (size_t)ray : nullptr);
+
+        // ---- stage 1 -----------------------------------------------------------------------------
+        proposal_stage<64, PL, GL, HG>(p, 1, sm, r, binsB, ds, lane);
+        weights_from_ds<64>(ds, lane, last_opaque);
+        __syncwarp();
+        sample_pdf_warp<64, 33>(ds, binsB, cdf, u33, binsA, lane, p.inds1 ? p.inds1 + 33 * (size_t)ray : nullptr);
+
+        // ---- stage 2: the radiance field, one sample per lane -----------------------------------
+        float tmid, delta, x01[3];
+        const bool inside = sample_point(r, binsA[lane], binsA[lane + 1], tmid, delta, x01);
+        float f16[16];  // grid_mlp output: [0] log-density, [1..15] geo_feat
+        {
+            float feat[2 * GL];
+            if (inside) {
+#pragma unroll
+                for (int l = 0; l < GL; l++) {
+                    float o[2];
+                    encode_level<2>(p.grid, l, x01, o);
+                    feat[2 * l] = o[0];
+                    feat[2 * l + 1] = o[1];
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < 2 * GL; k++) feat[k] = 0.f;
+            }
+            float h1[HG];
+            dense<2 * GL, 2 * GL, HG, true>(sm + S::grid_w0, feat, h1);
+#pragma unroll
+            for (int o = 0; o < 16; o++) f16[o] = 0.f;
+            // second hidden layer in blocks of 16 units, folded straight into the output layer so
+            // only h1 + one block are live (register budget)
+#pragma unroll
+            for (int nb = 0; nb < HG / 16; nb++) {
+                float a[16];
+#pragma unroll
+                for (int nn = 0; nn < 16; nn++) {
+                    float acc = 0.f;
+                    const float* wr = sm + S::grid_w1 + (nb * 16 + nn) * HG;
+#pragma unroll
+                    for (int k = 0; k < HG; k += 4) {
+                        const float4 w = *reinterpret_cast<const float4*>(wr + k);
+                        acc = __fmaf_rn(w.x, h1[k], acc); acc = __fmaf_rn(w.y, h1[k + 1], acc);
+                        acc = __fmaf_rn(w.z, h1[k + 2], acc); acc = __fmaf_rn(w.w, h1[k + 3], acc);
+                    }
+                    a[nn] = fmaxf(acc, 0.f);
+                }
+#pragma unroll
+                for (int o = 0; o < 16; o++) {
+                    const float* wr = sm + S::grid_w2 + o * HG + nb * 16;
+#pragma unroll
+                    for (int k = 0; k < 16; k += 4) {
+                        const float4 w = *reinterpret_cast<const float4*>(wr + k);
+                        f16[o] = __fmaf_rn(w.x, a[k], f16[o]); f16[o] = __fmaf_rn(w.y, a[k + 1], f16[o]);
+                        f16[o] = __fmaf_rn(w.z, a[k + 2], f16[o]); f16[o] = __fmaf_rn(w.w, a[k + 3], f16[o]);
+                    }
+                }
+            }
+        }
+        const float sigma = expf(f16[0]);
+        ds[lane] = __fmul_rn(delta, sigma);
+        __syncwarp();
+        weights_from_ds<32>(ds, lane, last_opaque);
+        __syncwarp();
+        const float w = ds[lane];
+        __syncwarp();
+
+        // ---- composite (renderer.py:333-340, 353) ------------------------------------------------
+        const float wsum = warp_sum(w);
+        const float depth = warp_sum(__fmul_rn(w, tmid));
+        float fimg[31];
+#pragma unroll
+        for (int c = 0; c < 15; c++) fimg[c] = warp_sum(__fmul_rn(w, f16[c + 1]));
+        {
+            // dirs = d/|d| (renderer.py:293-294), normalised once more by SHEncoder.forward
+            // (sphere_harmonics.py:82); the direction is per ray, so sum_j w_j*sh = wsum*sh
+            const float n1 = sqrtf(r.dx * r.dx + r.dy * r.dy + r.dz * r.dz);
+            float ux = __fdiv_rn(r.dx, n1), uy = __fdiv_rn(r.dy, n1), uz = __fdiv_rn(r.dz, n1);
+            const float n2 = sqrtf(ux * ux + uy * uy + uz * uz);
+            ux = __fdiv_rn(ux, n2); uy = __fdiv_rn(uy, n2); uz = __fdiv_rn(uz, n2);
+            float sh[16];
+            sh4(ux, uy, uz, sh);
+#pragma unroll
+            for (int c = 0; c < 16; c++) fimg[15 + c] = wsum * sh[c];
+        }
+        // deferred view MLP 31 -> Hv -> Hv -> 3: hidden unit `lane` per lane (rows >= Hv are zero)
+        float h1 = 0.f;
+        {
+            const float* wr = sm + S::view_w0 + lane * S::VP;
+#pragma unroll
+            for (int k = 0; k < 31; k++) h1 = __fmaf_rn(wr[k], fimg[k], h1);
+            h1 = fmaxf(h1, 0.f);
+        }
+        float h2 = 0.f;
+        {
+            const float* wr = sm + S::view_w1 + lane * S::VP;
+#pragma unroll
+            for (int k = 0; k < 32; k++) h2 = __fmaf_rn(wr[k], __shfl_sync(kFull, h1, k), h2);
+            h2 = fmaxf(h2, 0.f);
+        }
+        float rgb[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            const float o = warp_sum(sm[S::view_w2 + c * 32 + lane] * h2);
+            const float s = __fdiv_rn(1.0f, 1.0f + expf(-o));                       // sigmoid
+            const float bg = p.bg ? __ldg(p.bg + (p.bg_rows > 1 ? 3 * (size_t)ray : 0) + c) : p.bg_scalar;
+            rgb[c] = __fadd_rn(s, __fmul_rn(__fsub_rn(1.0f, wsum), bg));            // renderer.py:353
+        }
+        if (lane < 3) p.image[3 * (size_t)ray + lane] = lane == 0 ? rgb[0] : (lane == 1 ? rgb[1] : rgb[2]);
+        if (lane == 3) p.depth[ray] = depth;
+        if (lane == 4) p.wsum[ray] = wsum;
+
+        // ---- parity taps ------------------------------------------------------------------------
+        if (p.weights2) p.weights2[32 * (size_t)ray + lane] = w;
+        if (p.sigma2) p.sigma2[32 * (size_t)ray + lane] = sigma;
+        if (p.bins2) {
+            p.bins2[33 * (size_t)ray + lane] = binsA[lane];
+            if (lane == 0) p.bins2[33 * (size_t)ray + 32] = binsA[32];
+        }
+        if (p.f_image && lane < 31) {
+            float v = fimg[0];
+#pragma unroll
+            for (int c = 1; c < 31; c++) v = lane == c ? fimg[c] : v;
+            p.f_image[31 * (size_t)ray + lane] = v;
+        }
+
+        // ---- SAM feature head input (renderer.py:301-302, 361-367) --------------------------------
+        if constexpr (SAM) {
+            float* dst = p.sam_in + (size_t)ray * (8 * p.sgrid.L + 35);
+            const int nl = (int)p.sgrid.L;
+#pragma unroll 1
+            for (int l = 0; l < nl; l++) {
+                float o[8];
+                if (inside) {
+                    encode_level<8>(p.sgrid, l, x01, o);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) o[c] = 0.f;
+                }
+                float keep = 0.f;
+#pragma unroll
+                for (int c = 0; c < 8; c++) {
+                    const float s = warp_sum(__fmul_rn(w, o[c]));
+                    keep = lane == c ? s : keep;
+                }
+                if (lane < 8) dst[8 * l + lane] = keep;
+            }
+            float* tail = dst + 8 * nl;
+            if (lane < 31) {
+                float v = fimg[0];
+#pragma unroll
+                for (int c = 1; c < 31; c++) v = lane == c ? fimg[c] : v;
+                tail[lane] = v;
+            }
+            if (lane == 31) tail[34] = depth;
+            if (lane < 3) tail[31 + lane] = lane == 0 ? rgb[0] : (lane == 1 ? rgb[1] : rgb[2]);
+        }
+        // ---- object head input: per-sample cat[m_grid(x), geo_feat] (renderer.py:304-305, 378) ---
+        if constexpr (MASK) {
+            const int nl = (int)p.mgrid.L;
+            float* dst = p.mask_in + ((size_t)ray * 32 + lane) * (8 * nl + 15);
+#pragma unroll 1
+            for (int l = 0; l < nl; l++) {
+                float o[8];
+                if (inside) {
+                    encode_level<8>(p.mgrid, l, x01, o);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < 8; c++) o[c] = 0.f;
+                }
+#pragma unroll
+                for (int c = 0; c < 8; c++) dst[8 * l + c] = o[c];
+            }
+#pragma unroll
+            for (int c = 0; c < 15; c++) dst[8 * nl + c] = f16[c + 1];
+        }
+        __syncwarp();
+    }
+}
+
+// standalone sample_pdf (parity tests of the index buffers): one warp per ray
+template <int T0, int TN>
+__global__ void __launch_bounds__(256) sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights,
+                                                          const float* __restrict__ u, uint32_t N, float* __restrict__ new_bins,
+                                                          int16_t* __restrict__ inds) {
+    __shared__ float s_u[68];
+    __shared__ float s_w[8][128], s_b[8][132], s_c[8][132], s_o[8][68];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < TN; i += blockDim.x) s_u[i] = u[i];
+    __syncthreads();
+    const uint32_t ray = blockIdx.x * 8 + warp;
+    if (ray >= N) return;
+    for (int j = lane; j < T0; j += 32) s_w[warp][j] = weights[(size_t)ray * T0 + j];
+    for (int j = lane; j <= T0; j += 32) s_b[warp][j] = bins[(size_t)ray * (T0 + 1) + j];
+    __syncwarp();
+    sample_pdf_warp<T0, TN>(s_w[warp], s_b[warp], s_c[warp], s_u, s_o[warp], lane, inds ? inds + (size_t)ray * TN : nullptr);
+    for (int k = lane; k < TN; k += 32) new_bins[(size_t)ray * TN + k] = s_o[warp][k];
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+static int fill_grid(GridDev& g, const sanerf_grid_t& s, uint32_t C_expected) {
+    g.emb = s.embeddings;
+    g.L = s.num_levels;
+    g.C = s.level_dim;
+    if (!s.embeddings || s.num_levels == 0 || s.num_levels > SANERF_MAX_LEVELS || s.level_dim != C_expected) return SANERF_E_CONFIG;
+    for (uint32_t l = 0; l < s.num_levels; l++) {
+        const uint32_t rows = s.offset[l + 1] - s.offset[l], res = s.res[l];
+        if (res < 2 || rows == 0) return SANERF_E_CONFIG;
+        // the reference's dense-vs-hash decision (gridencoder.cu:61-79) for D=3, gridtype hash
+        uint64_t stride = 1;
+        for (int d = 0; d < 3 && stride <= rows; d++) stride *= res;
+        g.off[l] = s.offset[l];
+        g.res[l] = res;
+        if (stride <= rows) {
+            g.hmask[l] = 0;  // dense, index < res^3 <= rows
+        } else {
+            if (rows & (rows - 1)) return SANERF_E_CONFIG;  // hashed levels have 2^T rows (grid.py:129)
+            g.hmask[l] = rows - 1;
+        }
+    }
+    for (uint32_t l = s.num_levels; l < SANERF_MAX_LEVELS; l++) g.off[l] = g.res[l] = g.hmask[l] = 0;
+    return 0;
+}
+
+template <int PL, int GL, int HG, int HV>
+static int launch_render(const RenderParams& p, bool sam, bool mask, cudaStream_t st) {
+    using S = Smem<PL, GL, HG>;
+    const size_t smem = (size_t)S::total * sizeof(float);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t need = div_up(p.N, (uint32_t)kWarps);
+    const uint32_t blocks = need < (uint32_t)sms ? need : (uint32_t)sms;
+#define SANERF_LAUNCH(SAM_, MASK_)                                                                              \
+    do {                                                                                                        \
+        auto kfn = render_kernel<PL, GL, HG, HV, SAM_, MASK_>;                                                  \
+        if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
+            cudaGetLastError();                                                                                 \
+            return SANERF_E_SMEM;                                                                               \
+        }                                                                                                       \
+        kfn<<<blocks, kThreads, smem, st>>>(p);                                                                 \
+    } while (0)
+    if (sam && mask) SANERF_LAUNCH(true, true);
+    else if (sam) SANERF_LAUNCH(true, false);
+    else if (mask) SANERF_LAUNCH(false, true);
+    else SANERF_LAUNCH(false, false);
+#undef SANERF_LAUNCH
+    return check_launch();
+}
+
+}  // namespace sanerf
+
+using namespace sanerf;
+
+extern "C" {
+
+int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf_stream_t stream) {
+    if (!m || !a) return SANERF_E_NULL;
+    if (a->N == 0) return 0;
+    if (!a->rays_o || !a->rays_d || !a->image || !a->depth || !a->weights_sum || !m->u65 || !m->u33) return SANERF_E_NULL;
+    RenderParams p;
+    int rc;
+    if ((rc = fill_grid(p.prop[0], m->prop_grid[0], 2))) return rc;
+    if ((rc = fill_grid(p.prop[1], m->prop_grid[1], 2))) return rc;
+    if ((rc = fill_grid(p.grid, m->grid, 2))) return rc;
+    const bool sam = a->sam_in != nullptr, mask = a->mask_in != nullptr;
+    if (sam) { if ((rc = fill_grid(p.sgrid, m->s_grid, 8))) return rc; } else { p.sgrid = GridDev{}; }
+    if (mask) { if ((rc = fill_grid(p.mgrid, m->m_grid, 8))) return rc; } else { p.mgrid = GridDev{}; }
+    for (int i = 0; i < 2; i++) {
+        p.prop_w0[i] = m->prop_w0[i];
+        p.prop_w1[i] = m->prop_w1[i];
+        if (!p.prop_w0[i] || !p.prop_w1[i]) return SANERF_E_NULL;
+    }
+    for (int i = 0; i < 3; i++) {
+        p.grid_w[i] = m->grid_w[i];
+        p.view_w[i] = m->view_w[i];
+        if (!p.grid_w[i] || !p.view_w[i]) return SANERF_E_NULL;
+    }
+    for (int i = 0; i < 6; i++) p.aabb[i] = m->aabb[i];
+    p.min_near = m->min_near;
+    p.bound = m->grid_bound;
+    p.contract = m->contract;
+    p.last_opaque = m->last_sample_opaque;
+    p.u65 = m->u65;
+    p.u33 = m->u33;
+    p.rays_o = a->rays_o; p.rays_d = a->rays_d; p.N = a->N;
+    p.cnf = a->cam_near_far; p.cnf_rows = a->cam_near_far_rows;
+    p.bg = a->bg_color; p.bg_rows = a->bg_rows; p.bg_scalar = a->bg_scalar;
+    p.image = a->image; p.depth = a->depth; p.wsum = a->weights_sum;
+    p.sam_in = a->sam_in; p.mask_in = a->mask_in;
+    p.inds0 = a->inds0; p.inds1 = a->inds1; p.weights2 = a->weights2; p.sigma2 = a->sigma2; p.bins2 = a->bins2; p.f_image = a->f_image;
+
+    const uint32_t PL = m->prop_grid[0].num_levels, GL = m->grid.num_levels;
+    if (m->prop_grid[1].num_levels != PL) return SANERF_E_CONFIG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (PL == 5 && GL == 16 && m->grid_hidden == 64 && m->view_hidden == 32) return launch_render<5, 16, 64, 32>(p, sam, mask, st);
+    if (PL == 4 && GL == 4 && m->grid_hidden == 16 && m->view_hidden == 16) return launch_render<4, 4, 16, 16>(p, sam, mask, st);
+    return SANERF_E_CONFIG;
+}
+
+int sanerf_render_launch_count(const sanerf_model_t* m, const sanerf_render_args_t* a) {
+    (void)m;
+    return (a && a->N) ? 1 : 0;
+}
+
+int sanerf_sample_pdf(const float* bins, const float* weights, const float* u, uint32_t N, uint32_t T0, uint32_t T, float* new_bins,
+                      int16_t* inds, sanerf_stream_t stream) {
+    if (N == 0) return 0;
+    if (!bins || !weights || !u || !new_bins) return SANERF_E_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (T0 == 128 && T == 65) sample_pdf_kernel<128, 65><<<div_up(N, 8), 256, 0, st>>>(bins, weights, u, N, new_bins, inds);
+    else if (T0 == 64 && T == 33) sample_pdf_kernel<64, 33><<<div_up(N, 8), 256, 0, st>>>(bins, weights, u, N, new_bins, inds);
+    else return SANERF_E_CONFIG;
+    return check_launch();
+}
+
+int sanerf_abi_version(void) { return SANERF_ABI_VERSION; }
+
+const char* sanerf_error_string(int code) {
+    switch (code) {
+        case SANERF_OK: return "ok";
+        case SANERF_E_NULL: return "a required pointer is NULL";
+        case SANERF_E_DIM: return "GridEncoding: D must be 2, 3, 4 or 5 (SH / fused render: 3)";
+        case SANERF_E_CHANNELS: return "GridEncoding: C must be 1, 2, 4, 8, 16 or 32";
+        case SANERF_E_DEGREE: return "SH encoder only supports degree in [1, 8]";
+        case SANERF_E_CONFIG: return "fused render: unsupported model / shape combination";
+        case SANERF_E_SMEM: return "fused render: shared memory request rejected by the device";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown sanerf error";
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,465 @@
+"""Volumetric renderer (reference nerf/renderer.py:142-502) on top of libsanerf_b200.
+
+`NeRFRenderer.render / run` keep the reference's signature, keyword arguments and result dict.
+Two execution paths produce the same numbers:
+
+* fused   -- eval / no-grad, perturb=False (every eval, test, decode and GUI call of
+             nerf/trainer.py): ONE persistent CUDA launch (`sanerf_render`, csrc/render.cu) does
+             near/far, the three sampling stages with both proposal networks, sample_pdf,
+             contraction, hash-grid lookups, the density / geometry MLP, SH, compositing and the
+             deferred view MLP for all rays; `render(staged=True)` therefore does not chunk.
+* composed -- anything that needs autograd or random perturbation (training): the same algorithm
+             as differentiable torch ops around this package's CUDA encoders (forward+backward).
+
+There is no CPU path: rays must be CUDA tensors.
+"""
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+
+try:  # training-only dependency of the reference (renderer.py:14)
+    from torch_efficient_distloss import eff_distloss
+except ImportError:  # same O(T) prefix-sum formulation (Sun et al., DVGOv2), differentiable torch ops
+    def eff_distloss(w, m, interval):
+        loss_uni = (1 / 3) * (interval * w.pow(2)).sum(dim=-1).mean()
+        wm = w * m
+        w_cum, wm_cum = w.cumsum(dim=-1), wm.cumsum(dim=-1)
+        loss_bi = 2 * (wm[..., 1:] * w_cum[..., :-1] - w[..., 1:] * wm_cum[..., :-1]).sum(dim=-1).mean()
+        return loss_bi + loss_uni
+
+
+FUSED_NUM_STEPS = [128, 64, 32]
+
+
+def distort_loss(bins, weights):
+    """renderer.py:17-27"""
+    with torch.amp.autocast("cuda", enabled=False):
+        intervals = bins[..., 1:] - bins[..., :-1]
+        mid = bins[..., :-1] + intervals / 2
+        return eff_distloss(weights, mid, intervals)
+
+
+def proposal_loss(all_bins, all_weights):
+    """Inter-level (Mip-NeRF 360) bound loss of the proposal weights (renderer.py:30-57)."""
+    with torch.amp.autocast("cuda", enabled=False):
+        t_ref, w_ref = all_bins[-1].detach(), all_weights[-1].detach()
+        total = 0
+        for t, w in zip(all_bins[:-1], all_weights[:-1]):
+            cw = torch.cat([torch.zeros_like(w[..., :1]), torch.cumsum(w, dim=-1)], dim=-1)
+            last = w.shape[-1] - 1
+            lo = (torch.searchsorted(t[..., :-1].contiguous(), t_ref[..., :-1].contiguous(), right=True) - 1).clamp(0, last)
+            hi = torch.searchsorted(t[..., 1:].contiguous(), t_ref[..., 1:].contiguous(), right=True).clamp(0, last)
+            bound = torch.take_along_dim(cw[..., 1:], hi, dim=-1) - torch.take_along_dim(cw[..., :-1], lo, dim=-1)
+            total = total + ((w_ref - bound).clamp(min=0) ** 2 / (w_ref + 1e-8)).mean()
+        return total
+
+
+def contract(x):
+    """L-inf scene contraction to (-2, 2) (renderer.py:60-69)."""
+    with torch.amp.autocast("cuda", enabled=False):
+        shape = x.shape
+        x = x.reshape(-1, shape[-1])
+        mag, idx = x.abs().max(1, keepdim=True)
+        scale = (1 / mag).repeat(1, shape[-1])
+        scale.scatter_(1, idx, (2 - 1 / mag) / mag)
+        return torch.where(mag < 1, x, x * scale).view(shape)
+
+
+def uncontract(z):
+    """Inverse of `contract` (renderer.py:72-81)."""
+    with torch.amp.autocast("cuda", enabled=False):
+        shape = z.shape
+        z = z.reshape(-1, shape[-1])
+        mag, idx = z.abs().max(1, keepdim=True)
+        scale = 1 / (2 - mag.repeat(1, shape[-1])).clamp(min=1e-8)
+        scale.scatter_(1, idx, 1 / (2 * mag - mag * mag).clamp(min=1e-8))
+        return torch.where(mag < 1, z, z * scale).view(shape)
+
+
+def sample_pdf(bins, weights, T, perturb=False):
+    """Inverse-CDF resampling of `T` bin edges (renderer.py:84-119). bins [N,T0+1], weights [N,T0]."""
+    with torch.amp.autocast("cuda", enabled=False):
+        N, T0 = weights.shape
+        weights = weights + 0.01
+        pdf = weights / torch.sum(weights, -1, keepdim=True)
+        cdf = torch.cumsum(pdf, -1).clamp(max=1)
+        cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+        u = torch.linspace(0.5 / T, 1 - 0.5 / T, steps=T).to(weights.device).expand(N, T)
+        if perturb:
+            u = u + (torch.rand_like(u) - 0.5) / T
+        u = u.contiguous()
+        inds = torch.searchsorted(cdf, u, right=True)
+        below, above = torch.clamp(inds - 1, 0, T0), torch.clamp(inds, 0, T0)
+        c0, c1 = torch.gather(cdf, -1, below), torch.gather(cdf, -1, above)
+        b0, b1 = torch.gather(bins, -1, below), torch.gather(bins, -1, above)
+        t = torch.clamp(torch.nan_to_num((u - c0) / (c1 - c0)), 0, 1)
+        return b0 + t * (b1 - b0)
+
+
+def near_far_from_aabb(rays_o, rays_d, aabb, min_near=0.05):
+    """Slab test against aabb[6] (renderer.py:122-139) -> near [N,1], far [N,1]; miss -> 1e9."""
+    with torch.amp.autocast("cuda", enabled=False):
+        tmin = (aabb[:3] - rays_o) / (rays_d + 1e-15)
+        tmax = (aabb[3:] - rays_o) / (rays_d + 1e-15)
+        near = torch.where(tmin < tmax, tmin, tmax).amax(dim=-1, keepdim=True)
+        far = torch.where(tmin > tmax, tmin, tmax).amin(dim=-1, keepdim=True)
+        miss = far < near
+        near = near.masked_fill(miss, 1e9)
+        far = far.masked_fill(miss, 1e9)
+        return torch.clamp(near, min=min_near), far
+
+
+def _spacing(x):
+    return torch.where(x < 1, x / 2, 1 - 1 / (2 * x))
+
+
+def _spacing_inv(x):
+    return torch.where(x < 0.5, 2 * x, 1 / (2 - 2 * x))
+
+
+class NeRFRenderer(nn.Module):
+    def __init__(self, opt):
+        super().__init__()
+        self.opt = opt
+        self.real_bound = opt.bound                       # world-space half extent for ray marching
+        self.bound = 2 if self.opt.contract else opt.bound  # grid query range
+        self.cascade = 1 + math.ceil(math.log2(self.bound))
+        self.min_near = opt.min_near
+        self.density_thresh = opt.density_thresh
+        box = torch.FloatTensor([-self.real_bound] * 3 + [self.real_bound] * 3)
+        self.register_buffer("aabb_train", box)
+        self.register_buffer("aabb_infer", box.clone())
+        self._u_tables = {}
+        self._aabb_host = (None, None)
+        # set False to force the composed (torch op by op) path everywhere -- used by parity tests
+        self.fused = True
+
+    def forward(self, x, d, **kwargs):
+        raise NotImplementedError()
+
+    def density(self, x, **kwargs):
+        raise NotImplementedError()
+
+    def update_aabb(self, aabb):
+        if not torch.is_tensor(aabb):
+            aabb = torch.from_numpy(aabb).float()
+        self.aabb_train = aabb.clamp(-self.real_bound, self.real_bound).to(self.aabb_train.device)
+        self.aabb_infer = self.aabb_train.clone()
+        print(f"[INFO] update_aabb: {self.aabb_train.cpu().numpy().tolist()}")
+
+    # ------------------------------------------------------------------------------------------
+    # public entry points
+    # ------------------------------------------------------------------------------------------
+    def render(self, rays_o, rays_d, staged=False, cam_near_far=None, **kwargs):
+        """rays_o, rays_d [N,3] -> dict(image [N,3], depth [N], weights_sum [N], ...) (renderer.py:185-219)."""
+        if not staged:
+            # reference quirk kept for identical results: `cam_near_far` is swallowed by this signature and NOT
+            # forwarded in the non-staged call (renderer.py:187-188)
+            return self.run(rays_o, rays_d, **kwargs)
+        if self._can_fuse(rays_o, kwargs) and not kwargs.get("return_feats", 0):
+            # one persistent launch over all rays; max_ray_batch chunking only bounds the temporaries of the
+            # object head
+            return self._run_fused(rays_o, rays_d, cam_near_far=cam_near_far, **kwargs)
+        N, device = rays_o.shape[0], rays_o.device
+        results = {}
+        step = self.opt.max_ray_batch
+        for head in range(0, N, step):
+            tail = min(head + step, N)
+            cnf = cam_near_far
+            if cnf is not None and cnf.shape[0] != 1:
+                cnf = cnf[head:tail]
+            part = self.run(rays_o[head:tail], rays_d[head:tail], cam_near_far=cnf, **kwargs)
+            for k, v in part.items():
+                if v is None:
+                    continue
+                if torch.is_tensor(v):
+                    if k not in results:
+                        results[k] = torch.empty(N, *v.shape[1:], device=device)
+                    results[k][head:tail] = v
+                else:
+                    results[k] = v
+        return results
+
+    def run(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
+            return_feats=0, return_mask=0, H=None, W=None, **kwargs):
+        if self.opt.render_mesh:
+            return {}  # the reference's mesh branch is commented out and returns an empty dict (renderer.py:386-498)
+        kw = dict(bg_color=bg_color, perturb=perturb, cam_near_far=cam_near_far, update_proposal=update_proposal,
+                  return_feats=return_feats, return_mask=return_mask, H=H, W=W)
+        if self._can_fuse(rays_o, kw):
+            return self._run_fused(rays_o, rays_d, **kw)
+        return self._run_composed(rays_o, rays_d, **kw)
+
+    # ------------------------------------------------------------------------------------------
+    # fused path
+    # ------------------------------------------------------------------------------------------
+    def _can_fuse(self, rays_o, kw):
+        if not self.fused or not rays_o.is_cuda:
+            return False
+        if torch.is_grad_enabled() or kw.get("perturb", False):
+            return False
+        if self.opt.render_mesh or list(self.opt.num_steps) != FUSED_NUM_STEPS:
+            return False
+        if self.training and not self.opt.with_mask and not self.opt.with_sam:
+            return False  # rgb training mode also returns losses / weights (renderer.py:343-351)
+        if self.opt.with_sam and not self.opt.sam_use_view_direction:
+            return False
+        if kw.get("return_mask", 0) and self.opt.mask_mlp_type != "default":
+            return False
+        L = self.grid.num_levels
+        shape_ok = (L, self.prop_encoders[0].num_levels, self.grid_mlp.dim_hidden, self.view_mlp.dim_hidden) in (
+            (16, 5, 64, 32), (4, 4, 16, 16))
+        return shape_ok and self.prop_encoders[1].num_levels == self.prop_encoders[0].num_levels
+
+    def _u_table(self, T, device):
+        key = (T, str(device))
+        if key not in self._u_tables:  # the reference builds u on the CPU and copies it over (renderer.py:97)
+            self._u_tables[key] = torch.linspace(0.5 / T, 1 - 0.5 / T, steps=T).to(device)
+        return self._u_tables[key]
+
+    @staticmethod
+    def _fill_grid(dst, enc):
+        dst.embeddings = enc.embeddings.data_ptr()
+        dst.num_levels = enc.num_levels
+        dst.level_dim = enc.level_dim
+        for i, o in enumerate(enc.offsets_host):
+            dst.offset[i] = o
+        for i, r in enumerate(enc.level_resolutions()):
+            dst.res[i] = r
+
+    def _model_struct(self, device):
+        m = _lib.ModelT()
+        keep = []
+        for i in range(2):
+            self._fill_grid(m.prop_grid[i], self.prop_encoders[i])
+            m.prop_w0[i] = self.prop_mlp[i].net[0].weight.data_ptr()
+            m.prop_w1[i] = self.prop_mlp[i].net[1].weight.data_ptr()
+        self._fill_grid(m.grid, self.grid)
+        for i in range(3):
+            m.grid_w[i] = self.grid_mlp.net[i].weight.data_ptr()
+            m.view_w[i] = self.view_mlp.net[i].weight.data_ptr()
+        m.grid_hidden = self.grid_mlp.dim_hidden
+        m.view_hidden = self.view_mlp.dim_hidden
+        if self.opt.with_sam:
+            self._fill_grid(m.s_grid, self.s_grid)
+        if self.opt.with_mask and self.opt.mask_mlp_type == "default":
+            self._fill_grid(m.m_grid, self.m_grid)
+            m.n_inst = self.opt.n_inst
+        box = self.aabb_train if self.training else self.aabb_infer
+        key = (box.data_ptr(), box._version)
+        if self._aabb_host[0] != key:  # host copy cached so a render call does not sync the stream
+            self._aabb_host = (key, box.tolist())
+        aabb = self._aabb_host[1]
+        for i in range(6):
+            m.aabb[i] = aabb[i]
+        m.min_near = self.min_near
+        m.grid_bound = float(self.bound)
+        m.contract = int(bool(self.opt.contract))
+        m.last_sample_opaque = int(self.opt.background == "last_sample")
+        u65, u33 = self._u_table(65, device), self._u_table(33, device)
+        m.u65, m.u33 = u65.data_ptr(), u33.data_ptr()
+        keep += [u65, u33]
+        return m, keep
+
+    @torch.no_grad()
+    def _run_fused(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
+                   return_feats=0, return_mask=0, H=None, W=None, taps=None, **kwargs):
+        rays_o = rays_o.contiguous().float()
+        rays_d = rays_d.contiguous().float()
+        _lib.require_cuda(rays_o, rays_d, what="NeRFRenderer.run")
+        N, device = rays_o.shape[0], rays_o.device
+        lib = _lib.load()
+        for q in self.parameters():
+            if q.device != device:
+                raise RuntimeError("NeRFRenderer.run: model and rays must be on the same CUDA device")
+            break
+        model, keep = self._model_struct(device)
+
+        image = torch.empty(N, 3, device=device)
+        depth = torch.empty(N, device=device)
+        weights_sum = torch.empty(N, device=device)
+        results = {"weights_sum": weights_sum, "depth": depth, "image": image}
+
+        a = _lib.RenderArgsT()
+        a.rays_o, a.rays_d, a.N = rays_o.data_ptr(), rays_d.data_ptr(), N
+        if cam_near_far is not None:
+            cnf = cam_near_far.to(device=device, dtype=torch.float32).contiguous()
+            keep.append(cnf)
+            a.cam_near_far, a.cam_near_far_rows = cnf.data_ptr(), cnf.shape[0]
+        a.bg_scalar = 1.0
+        if bg_color is not None:
+            if torch.is_tensor(bg_color) and bg_color.numel() > 1:
+                bg = bg_color.to(device=device, dtype=torch.float32).reshape(-1, 3).contiguous()
+                keep.append(bg)
+                a.bg_color, a.bg_rows = bg.data_ptr(), bg.shape[0]
+            else:
+                a.bg_scalar = float(bg_color)
+        a.image, a.depth, a.weights_sum = image.data_ptr(), depth.data_ptr(), weights_sum.data_ptr()
+
+        want_sam = self.opt.with_sam and return_feats > 0
+        want_mask = return_mask > 0
+        if taps is not None:  # parity taps (tests): dict name -> None, filled with tensors
+            shapes = {"inds0": ((N, 65), torch.int16), "inds1": ((N, 33), torch.int16), "weights2": ((N, 32), torch.float32),
+                      "sigma2": ((N, 32), torch.float32), "bins2": ((N, 33), torch.float32), "f_image": ((N, 31), torch.float32)}
+            for name in list(taps):
+                shp, dt = shapes[name]
+                taps[name] = torch.empty(shp, device=device, dtype=dt)
+                setattr(a, name, taps[name].data_ptr())
+
+        if not want_mask:
+            sam_in = None
+            if want_sam:
+                sam_in = torch.empty(N, self.samvit_mlp[0].dim_in, device=device)
+                a.sam_in = sam_in.data_ptr()
+            with torch.cuda.device(device):
+                _lib.check(lib.sanerf_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "sanerf_render")
+                _lib.count_launch()
+            if want_sam:
+                results["samvit"] = self._samvit_head(sam_in).view(H, W, -1)
+            return results
+
+        # object head: per-sample mask_mlp inputs are materialised chunk-wise to bound memory
+        n_inst = self.opt.n_inst
+        logits = torch.empty(N, n_inst, device=device)
+        width = self.mask_mlp[0].dim_in
+        chunk = max(1, min(N, int(getattr(self.opt, "max_ray_batch", 4096)) * 8))
+        mask_in = torch.empty(chunk, 32, width, device=device)
+        w2 = torch.empty(chunk, 32, device=device)
+        sam_full = torch.empty(N, self.samvit_mlp[0].dim_in, device=device) if want_sam else None
+        base = {f: getattr(a, f) for f in ("rays_o", "rays_d", "image", "depth", "weights_sum", "cam_near_far", "bg_color",
+                                           "inds0", "inds1", "weights2", "sigma2", "bins2", "f_image")}
+        strides = {"rays_o": 12, "rays_d": 12, "image": 12, "depth": 4, "weights_sum": 4, "inds0": 130, "inds1": 66,
+                   "weights2": 128, "sigma2": 128, "bins2": 132, "f_image": 124}
+        user_w2 = base["weights2"]
+        for head in range(0, N, chunk):
+            n = min(chunk, N - head)
+            for f, s in strides.items():
+                if base[f]:
+                    setattr(a, f, base[f] + head * s)
+            if base["cam_near_far"] and a.cam_near_far_rows > 1:
+                a.cam_near_far = base["cam_near_far"] + head * 8
+            if base["bg_color"] and a.bg_rows > 1:
+                a.bg_color = base["bg_color"] + head * 12
+            a.N = n
+            a.mask_in = mask_in.data_ptr()
+            if not user_w2:
+                a.weights2 = w2.data_ptr()
+            if want_sam:
+                a.sam_in = sam_full.data_ptr() + head * sam_full.shape[1] * 4
+            with torch.cuda.device(device):
+                _lib.check(lib.sanerf_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "sanerf_render")
+                _lib.count_launch()
+            wts = taps["weights2"][head:head + n] if user_w2 else w2[:n]
+            point_masks = self.mask_mlp(mask_in[:n])
+            logits[head:head + n] = torch.sum(wts.unsqueeze(-1) * point_masks, dim=-2)
+        if want_sam:
+            results["samvit"] = self._samvit_head(sam_full).view(H, W, -1)
+        results["instance_mask_logits"] = logits
+        return results
+
+    def _samvit_head(self, f):
+        return self.samvit_mlp(f)
+
+    # ------------------------------------------------------------------------------------------
+    # composed path (differentiable; also the perturb=True path)
+    # ------------------------------------------------------------------------------------------
+    def _run_composed(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
+                      return_feats=0, return_mask=0, H=None, W=None, **kwargs):
+        rays_o = rays_o.contiguous()
+        rays_d = rays_d.contiguous()
+        if not rays_o.is_cuda:
+            raise RuntimeError("NeRFRenderer.run: rays must be CUDA tensors (there is no CPU path)")
+        N, device = rays_o.shape[0], rays_o.device
+        opt = self.opt
+
+        near, far = near_far_from_aabb(rays_o, rays_d, self.aabb_train if self.training else self.aabb_infer, self.min_near)
+        if cam_near_far is not None:
+            near = torch.maximum(near, cam_near_far[:, [0]])
+            far = torch.minimum(far, cam_near_far[:, [1]])
+        if bg_color is None:
+            bg_color = 1
+        s_near, s_far = _spacing(near), _spacing(far)
+
+        collect = self.training
+        all_bins, all_weights = [], []
+        results = {}
+        bins = weights = None
+        n_stage = len(opt.num_steps)
+        for stage, T in enumerate(opt.num_steps):
+            if stage == 0:
+                bins = torch.linspace(0, 1, T + 1, device=device).unsqueeze(0).expand(N, -1)
+                if perturb:
+                    bins = (bins + (torch.rand_like(bins) - 0.5) / T).clamp(0, 1)
+            else:
+                bins = sample_pdf(bins, weights, T + 1, perturb).detach()
+            real_bins = _spacing_inv(s_near * (1 - bins) + s_far * bins)          # [N, T+1] in [near, far]
+            rays_t = (real_bins[..., 1:] + real_bins[..., :-1]) / 2               # [N, T]
+            xyzs = rays_o.unsqueeze(1) + rays_d.unsqueeze(1) * rays_t.unsqueeze(2)
+            if opt.contract:
+                xyzs = contract(xyzs)
+
+            if stage != n_stage - 1:
+                with torch.set_grad_enabled(update_proposal and torch.is_grad_enabled()):
+                    sigmas = self.density(xyzs, proposal=stage)["sigma"]
+            else:
+                dirs = rays_d.view(-1, 1, 3).expand_as(xyzs)
+                dirs = dirs / torch.norm(dirs, dim=-1, keepdim=True)
+                out = self(xyzs, dirs)
+                sigmas, colors, geo_feat = out["sigma"], out["color"], out["geo_feat"]
+                if opt.with_sam:
+                    features = self.s_grid(xyzs, bound=self.bound)
+                if return_mask > 0 and opt.mask_mlp_type in ("default", "lightweight_mask"):
+                    masks = self.m_grid(xyzs, bound=self.bound)
+
+            deltas = real_bins[..., 1:] - real_bins[..., :-1]
+            ds = deltas * sigmas
+            if opt.background == "last_sample":                                   # opaque far plane
+                ds = torch.cat([ds[..., :-1], torch.full_like(ds[..., -1:], torch.inf)], dim=-1)
+            alphas = 1 - torch.exp(-ds)
+            acc = torch.cumsum(ds[..., :-1], dim=-1)
+            trans = torch.exp(-torch.cat([torch.zeros_like(acc[..., :1]), acc], dim=-1))
+            weights = (alphas * trans).nan_to_num_(0)
+            if collect:
+                all_bins.append(bins)
+                all_weights.append(weights)
+
+        weights_sum = torch.sum(weights, dim=-1)
+        depth = torch.sum(weights * rays_t, dim=-1)
+        f_image = torch.sum(weights.unsqueeze(-1) * colors, dim=-2)
+        image = torch.sigmoid(self.view_mlp(f_image))
+
+        if self.training and (not opt.with_mask and not opt.with_sam):
+            results["num_points"] = xyzs.shape[0] * xyzs.shape[1]
+            results["weights"] = weights
+            if opt.lambda_proposal > 0 and update_proposal:
+                results["proposal_loss"] = proposal_loss(all_bins, all_weights)
+            if opt.lambda_distort > 0:
+                results["distort_loss"] = distort_loss(bins, weights)
+
+        image = image + (1 - weights_sum).unsqueeze(-1) * bg_color
+        results["weights_sum"] = weights_sum
+        results["depth"] = depth
+        results["image"] = image
+
+        if opt.with_sam:
+            f_sam = torch.sum(weights.unsqueeze(-1) * features, dim=-2)
+            if opt.sam_use_view_direction:
+                f = torch.cat([f_sam, f_image, image, depth.unsqueeze(-1)], dim=-1)
+            else:
+                geo_sum = torch.sum(weights.unsqueeze(-1) * geo_feat, dim=-2)
+                f = torch.cat([f_sam, geo_sum, image, depth.unsqueeze(-1)], dim=-1)
+            samvit = self._samvit_head(f)
+            if return_feats > 0:
+                results["samvit"] = samvit.view(H, W, -1)
+
+        if return_mask > 0:
+            if opt.mask_mlp_type == "default":
+                point_masks = self.mask_mlp(torch.cat([masks, geo_feat.detach()], dim=-1))
+            elif opt.mask_mlp_type == "lightweight_mask":
+                point_masks = self.mask_mlp(torch.cat([masks, colors.detach()], dim=-1))
+            results["instance_mask_logits"] = torch.sum(weights.detach().unsqueeze(-1) * point_masks, dim=-2)
+        return results
