@@ -136,6 +136,14 @@ def test_grid_backward_tv_wd_match_oracle():
     y2 = enc(xs2, bound=1)
     w = torch.randn(y2.shape, generator=g).to(DEV)
     (y2 * w).sum().backward()
+    # exact check: grad_inputs[b,d] = sum_{l,c} grad[b,l,c] * dy_dx[b,l,d,c] with the oracle's analytic dy_dx
+    # (gridencoder.cu:352-378), then the chain rule of the (x+bound)/(2*bound) mapping (grid.py:156) = 1/2
+    x01_2 = (xs2.detach().cpu() + 1) / 2
+    dy_want = torch.zeros(64, L * 3 * C)
+    K.grid_encode_forward(x01_2, emb, sp.offsets, 64, 3, C, L, L, S, 16, dy_want)
+    want_gi = (w.cpu().view(64, L, 1, C) * dy_want.view(64, L, 3, C)).sum(dim=(1, 3)) / 2
+    assert rel_err(xs2.grad, want_gi, floor=1.0) < 1e-4
+    # sanity: central finite differences of the oracle agree wherever the stencil stays inside one cell of every level
     eps = 1e-4
     num = torch.zeros(64, 3)
     for d in range(3):
@@ -145,9 +153,8 @@ def test_grid_backward_tv_wd_match_oracle():
         fp = K.grid_encoder_apply(xp, emb, sp.offsets, sp.per_level_scale, 16, bound=1)
         fm = K.grid_encoder_apply(xm, emb, sp.offsets, sp.per_level_scale, 16, bound=1)
         num[:, d] = ((fp - fm) * w.cpu()).sum(-1) / (2 * eps)
-    # piecewise-linear interpolant: FD is exact inside a cell; allow the few points that straddle a cell face
     close = ((xs2.grad.cpu() - num).abs() <= 2e-2 * num.abs().clamp(min=1.0))
-    assert close.float().mean() > 0.9
+    assert close.float().mean() > 0.75   # ~10 % of the stencils straddle a cell face of some level at eps=1e-4
 
 
 def test_unsupported_shapes_raise_like_the_reference():
