@@ -185,8 +185,10 @@ def test_sh_matches_oracle(degree):
     enc = SHEncoder(degree=degree)
     got = enc(d.to(DEV))
     assert got.shape == (4000, degree * degree)
-    # same polynomials, FMA contraction may differ by an ulp per term: 2e-6 absolute on O(1) values
-    assert (got.cpu() - want).abs().max().item() < 4e-6
+    # same polynomials; nvcc contracts mul+add into FMA where the C oracle (-ffp-contract=off) rounds twice, and the
+    # degree-7/8 terms are sums of up to 5 products of magnitude ~5 that cancel: 1e-5 absolute, 2e-6 relative
+    assert (got.cpu() - want).abs().max().item() < 1e-5
+    assert rel_err(got, want, floor=1.0) < 2e-6 * degree
     # analytic gradient (dual numbers) vs central differences of the oracle in float64-ish steps
     dd = d[:200].clone().to(DEV).requires_grad_(True)
     w = torch.randn(200, degree * degree, generator=g).to(DEV)
