@@ -196,6 +196,13 @@ int sanerf_render_launch_count(const sanerf_model_t *model, const sanerf_render_
 int sanerf_sample_pdf(const float *bins, const float *weights, const float *u, uint32_t N, uint32_t T0,
                       uint32_t T, float *new_bins, int16_t *inds, sanerf_stream_t stream);
 
+/* Validation entry point for the tcgen05 (5th-gen tensor core) MLP path that the fused render uses for grid_mlp
+ * (nerf/network.py:9-29 `MLP`, bias-free, ReLU between layers): out[M,16] = relu(relu(x W0^T) W1^T) W2^T with
+ * x [M,K], W0 [H,K], W1 [H,H], W2 [16,H] in nn.Linear layout, fp32 in/out, split-precision (3xTF32) tensor-core math.
+ * Supported (K,H): (32,64) default network, (8,16) config #1, (16,32). */
+int sanerf_mlp3_tc(const float *x, const float *w0, const float *w1, const float *w2, float *out, uint32_t M, uint32_t K,
+                   uint32_t H, sanerf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

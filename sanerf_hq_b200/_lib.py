@@ -52,13 +52,11 @@ PROTOTYPES = {
     "sanerf_render": [ctypes.POINTER(ModelT), ctypes.POINTER(RenderArgsT), _vp],
     "sanerf_render_launch_count": [ctypes.POINTER(ModelT), ctypes.POINTER(RenderArgsT)],
     "sanerf_sample_pdf": [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp],
-    "sanerf_mlp_heads_workspace": [_u32, _u32],
-    "sanerf_samvit_mlp": [_vp, ctypes.POINTER(ModelT), _u32, _vp, _vp, _vp],
-    "sanerf_mask_mlp": [_vp, _vp, ctypes.POINTER(ModelT), _u32, _vp, _vp, _vp],
+    "sanerf_mlp3_tc": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp],
     "sanerf_abi_version": [],
     "sanerf_error_string": [_i32],
 }
-OPTIONAL = {"sanerf_mlp_heads_workspace", "sanerf_samvit_mlp", "sanerf_mask_mlp"}
+OPTIONAL = set()
 
 _lib = None
 

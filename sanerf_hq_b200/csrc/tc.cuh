@@ -1,0 +1,270 @@
+// tc.cuh -- thin inline-PTX layer over the Blackwell 5th-gen tensor core (tcgen05) for the tiny MLPs of the
+// render path (sm_100a).
+//
+// Shape of the problem: a "group" of 4 warps (128 threads) owns 128 rows (= samples), one row per thread,
+// which is exactly the TMEM datapath mapping: TMEM lane i <-> thread i of the group, and a warp may only touch
+// the 32 lanes of its own sub-partition (warp_id % 4).  A layer  D[128,N] = A[128,K] * W[N,K]^T  is
+//     tcgen05.st   (each thread writes its own A row into TMEM columns)      -- no shared-memory staging
+//     tcgen05.mma  .kind::tf32, A from TMEM, B = W from shared memory (K-major, no swizzle), D in TMEM
+//     tcgen05.ld   (each thread reads its own D row)
+// fp32 accuracy comes from split-precision operands (3xTF32):  A = Ah + Al,  W = Wh + Wl  (each exactly
+// representable in tf32),  D = Ah*Wh + Ah*Wl + Al*Wh  with fp32 accumulation in the tensor core; the dropped
+// Al*Wl term is 2^-22 relative.
+#pragma once
+#include <stdint.h>
+
+namespace sanerf {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- TMEM allocation (one warp, .sync.aligned) ----------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- ordering ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy writes to shared memory (st.shared) -> visible to the tensor core's async proxy
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_barrier(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---- mbarrier ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// all previously issued tcgen05.mma of this thread arrive on `bar` when they complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- descriptors --------------------------------------------------------------------------------------------
+// Shared-memory operand descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): core matrix = 8 rows x 16 B
+// stored contiguously (128 B); SBO = byte distance between core matrices adjacent along N, LBO = along K.
+__device__ __forceinline__ uint64_t smem_desc_kmajor(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
+}
+// Instruction descriptor for kind::tf32 (cute::UMMA::InstrDescriptor): D = f32, A = B = tf32, both K-major, M x N.
+__host__ __device__ constexpr uint32_t idesc_tf32(uint32_t M, uint32_t N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T ; one thread issues for the whole CTA
+__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// ---- TMEM <-> registers: shape 32x32b, thread i of the warp <-> lane (32*(warp%4) + i), 16 consecutive columns ---
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]),
+        "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+                 "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- split precision ----------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+    return r;
+}
+// residual x - hi (exact in fp32), itself rounded to tf32 (the tensor core would otherwise truncate it): |x - hi - lo| <= 2^-23 |x|
+__device__ __forceinline__ uint32_t tf32_lo(float x, uint32_t hi) { return tf32_hi(x - __uint_as_float(hi)); }
+
+// ---- weights in shared memory ---------------------------------------------------------------------------------
+// W [N,K] (nn.Linear layout, row n = output unit) is stored as the canonical K-major no-swizzle operand
+//     float index(n,k) = ((k/4)*N + n)*4 + k%4      (core matrix = 8 consecutive n x 4 consecutive k = 128 B)
+// so that LBO (next 4 k) = 16*N bytes and SBO (next 8 n) = 128 bytes; one MMA (K=8) starts at k-step ks:
+//     base + ks*2*16*N bytes.
+__host__ __device__ constexpr int w_index(int n, int k, int N) { return ((k >> 2) * N + n) * 4 + (k & 3); }
+
+// Stage W (global, [N,K] row-major, fp32) into hi / lo operand images (each N*KP floats, KP = K rounded up to 8; zero padded).
+template <int N, int K, int KP>
+__device__ __forceinline__ void stage_split_weights(float* s_hi, float* s_lo, const float* __restrict__ w, int tid, int nthreads) {
+    for (int i = tid; i < N * KP; i += nthreads) {
+        const int n = i / KP, k = i % KP;
+        const float v = k < K ? __ldg(w + n * K + k) : 0.f;
+        const uint32_t h = tf32_hi(v);
+        const uint32_t l = tf32_hi(v - __uint_as_float(h));
+        s_hi[w_index(n, k, N)] = __uint_as_float(h);
+        s_lo[w_index(n, k, N)] = __uint_as_float(l);
+    }
+}
+
+// Issue D[128,N] (+)= A[128,8*KSTEPS] * W^T for one operand image.  a_tmem: first column of A (lane field 0).
+template <int N, int KSTEPS>
+__device__ __forceinline__ void issue_layer(uint32_t d_tmem, uint32_t a_tmem, const float* s_w, uint32_t first_accumulate) {
+    constexpr uint32_t idesc = idesc_tf32(128, N);
+    const uint32_t wbase = smem_u32(s_w);
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ks++) {
+        const uint64_t bd = smem_desc_kmajor(wbase + ks * 2 * 16 * N, 16 * N, 128);
+        mma_tf32_ts(d_tmem, a_tmem + 8 * ks, bd, idesc, (ks > 0) ? 1u : first_accumulate);
+    }
+}
+
+}  // namespace tc
+}  // namespace sanerf
+
+// ================================================================================================================
+// Group MLP: 4 warps = 128 rows, one row per thread.  TMEM budget per group: 128 columns
+//     [0,64)   A operand (activations, tf32 hi [and lo when 2K <= 64])
+//     [64,128) D accumulator (fp32)
+// A layer with 2K <= 64 runs in one round (hi and lo side by side); a K = 64 layer runs in two rounds
+// (hi: D = Ah*Wh + Ah*Wl, then lo over the same columns: D += Al*Wh).
+// ================================================================================================================
+namespace sanerf {
+namespace tc {
+
+constexpr uint32_t kGroupCols = 128, kACols = 64;
+
+struct Group {
+    uint32_t a_mma, d_mma;  // TMEM addresses (lane field 0) of the A / D regions for the MMA
+    uint32_t a_rw, d_rw;    // same columns with this warp's lane base (32 * (warp % 4)) for tcgen05.ld / st
+    uint64_t* bar;          // mbarrier the MMAs commit to
+    uint32_t phase;         // parity of the next completion
+    uint32_t bar_id;        // named barrier of the group (128 threads)
+    bool issuer;            // the one thread of the group that issues tcgen05.mma
+};
+
+__device__ __forceinline__ Group make_group(uint32_t tmem_base, int group, int warp_in_group, int lane, uint64_t* bar) {
+    Group g;
+    g.a_mma = tmem_base + group * kGroupCols;
+    g.d_mma = g.a_mma + kACols;
+    g.a_rw = g.a_mma + ((uint32_t)(warp_in_group * 32) << 16);
+    g.d_rw = g.d_mma + ((uint32_t)(warp_in_group * 32) << 16);
+    g.bar = bar;
+    g.phase = 0;
+    g.bar_id = 1 + group;
+    g.issuer = (warp_in_group == 0 && lane == 0);
+    return g;
+}
+
+template <int K>
+__device__ __forceinline__ void st_cols(uint32_t taddr, const uint32_t (&v)[K]) {
+    static_assert(K % 8 == 0, "A rows are written 8 or 16 columns at a time");
+    if constexpr (K % 16 == 0) {
+#pragma unroll
+        for (int c = 0; c < K; c += 16) {
+            uint32_t t[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) t[i] = v[c + i];
+            tmem_st16(taddr + c, t);
+        }
+    } else {
+#pragma unroll
+        for (int c = 0; c < K; c += 8) {
+            uint32_t t[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) t[i] = v[c + i];
+            tmem_st8(taddr + c, t);
+        }
+    }
+}
+
+// wait for every thread's A row, let the issuer launch the MMAs, wait for them to complete
+template <class IssueFn>
+__device__ __forceinline__ void group_round(Group& g, IssueFn&& issue) {
+    tmem_st_wait();
+    fence_before_sync();
+    named_barrier(g.bar_id, 128);
+    if (g.issuer) {
+        fence_after_sync();
+        issue();
+        mma_commit(g.bar);
+    }
+    __syncwarp();
+    mbar_wait(g.bar, g.phase);
+    g.phase ^= 1;
+    fence_after_sync();
+}
+
+// d[N] = (RELU?) a[K] . W[N,K]^T for the 128 rows of the group; s_hi / s_lo = operand images of W (stage_split_weights)
+template <int K, int N, bool RELU>
+__device__ __forceinline__ void group_layer(Group& g, const float* s_hi, const float* s_lo, const float (&a)[K], float (&d)[N]) {
+    static_assert(K % 8 == 0 && K <= 64 && N % 16 == 0 && N <= 64, "layer shape");
+    const uint32_t d_mma = g.d_mma, a_mma = g.a_mma;
+    if constexpr (2 * K <= (int)kACols) {
+        uint32_t t[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) t[k] = tf32_hi(a[k]);
+        st_cols<K>(g.a_rw, t);
+#pragma unroll
+        for (int k = 0; k < K; k++) t[k] = tf32_lo(a[k], t[k]);
+        st_cols<K>(g.a_rw + K, t);
+        group_round(g, [&] {
+            issue_layer<N, K / 8>(d_mma, a_mma, s_hi, 0u);
+            issue_layer<N, K / 8>(d_mma, a_mma, s_lo, 1u);
+            issue_layer<N, K / 8>(d_mma, a_mma + K, s_hi, 1u);
+        });
+    } else {
+        uint32_t t[K];
+#pragma unroll
+        for (int k = 0; k < K; k++) t[k] = tf32_hi(a[k]);
+        st_cols<K>(g.a_rw, t);
+        group_round(g, [&] {
+            issue_layer<N, K / 8>(d_mma, a_mma, s_hi, 0u);
+            issue_layer<N, K / 8>(d_mma, a_mma, s_lo, 1u);
+        });
+#pragma unroll
+        for (int k = 0; k < K; k++) t[k] = tf32_lo(a[k], tf32_hi(a[k]));
+        st_cols<K>(g.a_rw, t);
+        group_round(g, [&] { issue_layer<N, K / 8>(d_mma, a_mma, s_hi, 1u); });
+    }
+#pragma unroll
+    for (int c = 0; c < N; c += 16) {
+        uint32_t t[16];
+        tmem_ld16(g.d_rw + c, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float v = __uint_as_float(t[i]);
+            d[c + i] = RELU ? fmaxf(v, 0.f) : v;
+        }
+    }
+}
+
+}  // namespace tc
+}  // namespace sanerf
