@@ -25,6 +25,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace sanerf {
 
@@ -217,10 +218,11 @@ struct Smem {
     // offsets in floats
     static constexpr int prop_w0 = 0;                        // [2][16][PKP]
     static constexpr int prop_w1 = prop_w0 + 2 * 16 * PKP;   // [2][16]
-    static constexpr int grid_w0 = prop_w1 + 2 * 16;         // [HG][GK]
-    static constexpr int grid_w1 = grid_w0 + HG * GK;        // [HG][HG]
-    static constexpr int grid_w2 = grid_w1 + HG * HG;        // [16][HG]
-    static constexpr int view_w0 = grid_w2 + 16 * HG;        // [32][VP]  (rows >= Hv zero)
+    // grid_mlp weights as tensor-core operand images (tc.cuh: K-major core matrices), tf32 hi part then lo part
+    static constexpr int grid_w0 = (prop_w1 + 2 * 16 + 31) & ~31;  // 2 x [HG][GK]   (128-byte aligned)
+    static constexpr int grid_w1 = grid_w0 + 2 * HG * GK;          // 2 x [HG][HG]
+    static constexpr int grid_w2 = grid_w1 + 2 * HG * HG;          // 2 x [16][HG]
+    static constexpr int view_w0 = grid_w2 + 2 * 16 * HG;          // [32][VP]  (rows >= Hv zero)
     static constexpr int view_w1 = view_w0 + 32 * VP;        // [32][VP]
     static constexpr int view_w2 = view_w1 + 32 * VP;        // [3][32]
     static constexpr int utab = view_w2 + 3 * 32;            // u65 (68 slots) + u33 (36 slots)
@@ -231,7 +233,7 @@ struct Smem {
     static constexpr int s_cdf = 392;     // [132]
     static constexpr int per_warp = 524;
     static constexpr int total = scratch + kWarps * per_warp;
-    static_assert(GK % 4 == 0 && HG % 16 == 0, "grid MLP widths");
+    static_assert(GK % 8 == 0 && GK <= 32 && HG % 16 == 0 && HG <= 64, "grid MLP widths (tc::group_layer)");
 };
 
 template <int PL, int GL, int HG, int HV>
@@ -243,9 +245,10 @@ __device__ void stage_weights(float* sm, const RenderParams& p) {
         sm[S::prop_w0 + i] = k < S::PK ? __ldg(p.prop_w0[e] + r * S::PK + k) : 0.f;
     }
     for (int i = tid; i < 32; i += kThreads) sm[S::prop_w1 + i] = __ldg(p.prop_w1[i / 16] + (i % 16));
-    for (int i = tid; i < HG * S::GK; i += kThreads) sm[S::grid_w0 + i] = __ldg(p.grid_w[0] + i);
-    for (int i = tid; i < HG * HG; i += kThreads) sm[S::grid_w1 + i] = __ldg(p.grid_w[1] + i);
-    for (int i = tid; i < 16 * HG; i += kThreads) sm[S::grid_w2 + i] = __ldg(p.grid_w[2] + i);
+    tc::stage_split_weights<HG, S::GK, S::GK>(sm + S::grid_w0, sm + S::grid_w0 + HG * S::GK, p.grid_w[0], tid, kThreads);
+    tc::stage_split_weights<HG, HG, HG>(sm + S::grid_w1, sm + S::grid_w1 + HG * HG, p.grid_w[1], tid, kThreads);
+    tc::stage_split_weights<16, HG, HG>(sm + S::grid_w2, sm + S::grid_w2 + 16 * HG, p.grid_w[2], tid, kThreads);
+    tc::fence_proxy_async_smem();  // the tensor core reads these through the async proxy
     for (int i = tid; i < 32 * S::VP; i += kThreads) {
         const int n = i / S::VP, k = i % S::VP;
         sm[S::view_w0 + i] = (n < HV && k < 31) ? __ldg(p.view_w[0] + n * 31 + k) : 0.f;
@@ -409,11 +412,22 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, con
 template <int PL, int GL, int HG, int HV, bool SAM, bool MASK>
 __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_constant__ RenderParams p) {
     using S = Smem<PL, GL, HG>;
-    extern __shared__ __align__(16) float sm[];
-    stage_weights<PL, GL, HG, HV>(sm, p);
-    __syncthreads();
-
+    extern __shared__ __align__(128) float sm[];
+    __shared__ __align__(8) uint64_t mma_bar[kWarps / 4];
+    __shared__ uint32_t tmem_base_s;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    stage_weights<PL, GL, HG, HV>(sm, p);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kWarps / 4; i++) tc::mbar_init(&mma_bar[i], 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);  // one persistent CTA per SM owns all 512 TMEM columns: 4 groups x 128
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    // 4 warps = 4 rays = 128 samples of the final stage form one tensor-core group (one MMA row per thread)
+    tc::Group grp = tc::make_group(tmem_base_s, warp >> 2, warp & 3, lane, &mma_bar[warp >> 2]);
+
     float* scratch = sm + S::scratch + warp * S::per_warp;
     float* binsA = scratch + S::s_bins;
     float* binsB = binsA + 132;
@@ -424,7 +438,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     const bool last_opaque = p.last_opaque != 0;
 
     const uint32_t total_warps = gridDim.x * kWarps;
-    for (uint32_t ray = blockIdx.x * kWarps + warp; ray < p.N; ray += total_warps) {
+    // every warp of the CTA runs the same number of iterations (the groups synchronise inside); a warp past the end
+    // re-renders the last ray and skips the stores
+    for (uint32_t base = blockIdx.x * kWarps; base < p.N; base += total_warps) {
+        const bool active = base + warp < p.N;
+        const uint32_t ray = active ? base + warp : p.N - 1;
         // ---- ray setup: near/far from the AABB (renderer.py:122-139, 231-235) -------------------
         RayCtx r;
         r.ox = __ldg(p.rays_o + 3 * (size_t)ray); r.oy = __ldg(p.rays_o + 3 * (size_t)ray + 1); r.oz = __ldg(p.rays_o + 3 * (size_t)ray + 2);
@@ -459,13 +477,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         proposal_stage<128, PL, GL, HG>(p, 0, sm, r, binsA, ds, lane);
         weights_from_ds<128>(ds, lane, last_opaque);
         __syncwarp();
-        sample_pdf_warp<128, 65>(ds, binsA, cdf, u65, binsB, lane, p.inds0 ? p.inds0 + 65 * (size_t)ray : nullptr);
+        sample_pdf_warp<128, 65>(ds, binsA, cdf, u65, binsB, lane, (p.inds0 && active) ? p.inds0 + 65 * (size_t)ray : nullptr);
 
         // ---- stage 1 -----------------------------------------------------------------------------
         proposal_stage<64, PL, GL, HG>(p, 1, sm, r, binsB, ds, lane);
         weights_from_ds<64>(ds, lane, last_opaque);
         __syncwarp();
-        sample_pdf_warp<64, 33>(ds, binsB, cdf, u33, binsA, lane, p.inds1 ? p.inds1 + 33 * (size_t)ray : nullptr);
+        sample_pdf_warp<64, 33>(ds, binsB, cdf, u33, binsA, lane, (p.inds1 && active) ? p.inds1 + 33 * (size_t)ray : nullptr);
 
         // ---- stage 2: the radiance field, one sample per lane -----------------------------------
         float tmid, delta, x01[3];
@@ -485,38 +503,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 #pragma unroll
                 for (int k = 0; k < 2 * GL; k++) feat[k] = 0.f;
             }
+            // grid_mlp 2L -> Hg -> Hg -> 16 (ReLU, no bias; network.py:94) on the tensor core: the 4 warps of the group put
+            // their 4 x 32 samples into the 128 TMEM lanes, tcgen05.mma (3xTF32 split precision) does the three layers
             float h1[HG];
-            dense<2 * GL, 2 * GL, HG, true>(sm + S::grid_w0, feat, h1);
-#pragma unroll
-            for (int o = 0; o < 16; o++) f16[o] = 0.f;
-            // second hidden layer in blocks of 16 units, folded straight into the output layer so
-            // only h1 + one block are live (register budget)
-#pragma unroll
-            for (int nb = 0; nb < HG / 16; nb++) {
-                float a[16];
-#pragma unroll
-                for (int nn = 0; nn < 16; nn++) {
-                    float acc = 0.f;
-                    const float* wr = sm + S::grid_w1 + (nb * 16 + nn) * HG;
-#pragma unroll
-                    for (int k = 0; k < HG; k += 4) {
-                        const float4 w = *reinterpret_cast<const float4*>(wr + k);
-                        acc = __fmaf_rn(w.x, h1[k], acc); acc = __fmaf_rn(w.y, h1[k + 1], acc);
-                        acc = __fmaf_rn(w.z, h1[k + 2], acc); acc = __fmaf_rn(w.w, h1[k + 3], acc);
-                    }
-                    a[nn] = fmaxf(acc, 0.f);
-                }
-#pragma unroll
-                for (int o = 0; o < 16; o++) {
-                    const float* wr = sm + S::grid_w2 + o * HG + nb * 16;
-#pragma unroll
-                    for (int k = 0; k < 16; k += 4) {
-                        const float4 w = *reinterpret_cast<const float4*>(wr + k);
-                        f16[o] = __fmaf_rn(w.x, a[k], f16[o]); f16[o] = __fmaf_rn(w.y, a[k + 1], f16[o]);
-                        f16[o] = __fmaf_rn(w.z, a[k + 2], f16[o]); f16[o] = __fmaf_rn(w.w, a[k + 3], f16[o]);
-                    }
-                }
-            }
+            tc::group_layer<2 * GL, HG, true>(grp, sm + S::grid_w0, sm + S::grid_w0 + HG * S::GK, feat, h1);
+            float h2[HG];
+            tc::group_layer<HG, HG, true>(grp, sm + S::grid_w1, sm + S::grid_w1 + HG * HG, h1, h2);
+            tc::group_layer<HG, 16, false>(grp, sm + S::grid_w2, sm + S::grid_w2 + 16 * HG, h2, f16);
         }
         const float sigma = expf(f16[0]);
         ds[lane] = __fmul_rn(delta, sigma);
@@ -567,18 +560,20 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             const float bg = p.bg ? __ldg(p.bg + (p.bg_rows > 1 ? 3 * (size_t)ray : 0) + c) : p.bg_scalar;
             rgb[c] = __fadd_rn(s, __fmul_rn(__fsub_rn(1.0f, wsum), bg));            // renderer.py:353
         }
-        if (lane < 3) p.image[3 * (size_t)ray + lane] = lane == 0 ? rgb[0] : (lane == 1 ? rgb[1] : rgb[2]);
-        if (lane == 3) p.depth[ray] = depth;
-        if (lane == 4) p.wsum[ray] = wsum;
+        if (active) {
+            if (lane < 3) p.image[3 * (size_t)ray + lane] = lane == 0 ? rgb[0] : (lane == 1 ? rgb[1] : rgb[2]);
+            if (lane == 3) p.depth[ray] = depth;
+            if (lane == 4) p.wsum[ray] = wsum;
+        }
 
         // ---- parity taps ------------------------------------------------------------------------
-        if (p.weights2) p.weights2[32 * (size_t)ray + lane] = w;
-        if (p.sigma2) p.sigma2[32 * (size_t)ray + lane] = sigma;
-        if (p.bins2) {
+        if (p.weights2 && active) p.weights2[32 * (size_t)ray + lane] = w;
+        if (p.sigma2 && active) p.sigma2[32 * (size_t)ray + lane] = sigma;
+        if (p.bins2 && active) {
             p.bins2[33 * (size_t)ray + lane] = binsA[lane];
             if (lane == 0) p.bins2[33 * (size_t)ray + 32] = binsA[32];
         }
-        if (p.f_image && lane < 31) {
+        if (p.f_image && active && lane < 31) {
             float v = fimg[0];
 #pragma unroll
             for (int c = 1; c < 31; c++) v = lane == c ? fimg[c] : v;
@@ -586,7 +581,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         }
 
         // ---- SAM feature head input (renderer.py:301-302, 361-367) --------------------------------
-        if constexpr (SAM) {
+        if constexpr (SAM) if (active) {
             float* dst = p.sam_in + (size_t)ray * (8 * p.sgrid.L + 35);
             const int nl = (int)p.sgrid.L;
 #pragma unroll 1
@@ -617,7 +612,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             if (lane < 3) tail[31 + lane] = lane == 0 ? rgb[0] : (lane == 1 ? rgb[1] : rgb[2]);
         }
         // ---- object head input: per-sample cat[m_grid(x), geo_feat] (renderer.py:304-305, 378) ---
-        if constexpr (MASK) {
+        if constexpr (MASK) if (active) {
             const int nl = (int)p.mgrid.L;
             float* dst = p.mask_in + ((size_t)ray * 32 + lane) * (8 * nl + 15);
 #pragma unroll 1
@@ -637,6 +632,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         }
         __syncwarp();
     }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem_base_s, 512);
 }
 
 // standalone sample_pdf (parity tests of the index buffers): one warp per ray

@@ -182,25 +182,22 @@ __device__ __forceinline__ Group make_group(uint32_t tmem_base, int group, int w
     return g;
 }
 
-template <int K>
-__device__ __forceinline__ void st_cols(uint32_t taddr, const uint32_t (&v)[K]) {
+// write hi (PART 0) or lo (PART 1) parts of a[K] into K consecutive TMEM columns, 8/16 columns per instruction so that
+// only one chunk of converted values is live at a time
+template <int K, int PART>
+__device__ __forceinline__ void st_split(uint32_t taddr, const float (&a)[K]) {
     static_assert(K % 8 == 0, "A rows are written 8 or 16 columns at a time");
-    if constexpr (K % 16 == 0) {
+    constexpr int CH = (K % 16 == 0) ? 16 : 8;
 #pragma unroll
-        for (int c = 0; c < K; c += 16) {
-            uint32_t t[16];
+    for (int c = 0; c < K; c += CH) {
+        uint32_t t[CH];
 #pragma unroll
-            for (int i = 0; i < 16; i++) t[i] = v[c + i];
-            tmem_st16(taddr + c, t);
+        for (int i = 0; i < CH; i++) {
+            const uint32_t h = tf32_hi(a[c + i]);
+            t[i] = PART == 0 ? h : tf32_lo(a[c + i], h);
         }
-    } else {
-#pragma unroll
-        for (int c = 0; c < K; c += 8) {
-            uint32_t t[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) t[i] = v[c + i];
-            tmem_st8(taddr + c, t);
-        }
+        if constexpr (CH == 16) tmem_st16(taddr + c, t);
+        else tmem_st8(taddr + c, t);
     }
 }
 
@@ -227,30 +224,20 @@ __device__ __forceinline__ void group_layer(Group& g, const float* s_hi, const f
     static_assert(K % 8 == 0 && K <= 64 && N % 16 == 0 && N <= 64, "layer shape");
     const uint32_t d_mma = g.d_mma, a_mma = g.a_mma;
     if constexpr (2 * K <= (int)kACols) {
-        uint32_t t[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) t[k] = tf32_hi(a[k]);
-        st_cols<K>(g.a_rw, t);
-#pragma unroll
-        for (int k = 0; k < K; k++) t[k] = tf32_lo(a[k], t[k]);
-        st_cols<K>(g.a_rw + K, t);
+        st_split<K, 0>(g.a_rw, a);
+        st_split<K, 1>(g.a_rw + K, a);
         group_round(g, [&] {
             issue_layer<N, K / 8>(d_mma, a_mma, s_hi, 0u);
             issue_layer<N, K / 8>(d_mma, a_mma, s_lo, 1u);
             issue_layer<N, K / 8>(d_mma, a_mma + K, s_hi, 1u);
         });
     } else {
-        uint32_t t[K];
-#pragma unroll
-        for (int k = 0; k < K; k++) t[k] = tf32_hi(a[k]);
-        st_cols<K>(g.a_rw, t);
+        st_split<K, 0>(g.a_rw, a);
         group_round(g, [&] {
             issue_layer<N, K / 8>(d_mma, a_mma, s_hi, 0u);
             issue_layer<N, K / 8>(d_mma, a_mma, s_lo, 1u);
         });
-#pragma unroll
-        for (int k = 0; k < K; k++) t[k] = tf32_lo(a[k], tf32_hi(a[k]));
-        st_cols<K>(g.a_rw, t);
+        st_split<K, 1>(g.a_rw, a);
         group_round(g, [&] { issue_layer<N, K / 8>(d_mma, a_mma, s_hi, 1u); });
     }
 #pragma unroll
