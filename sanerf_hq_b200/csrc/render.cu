@@ -100,8 +100,9 @@ __device__ __forceinline__ float nan_to_num0(float x) {
 }
 
 // spacing_fn / spacing_fn_inv (renderer.py:249-252)
-__device__ __forceinline__ float spacing(float x) { return x < 1.0f ? x * 0.5f : __fsub_rn(1.0f, __fdiv_rn(1.0f, 2.0f * x)); }
-__device__ __forceinline__ float spacing_inv(float x) { return x < 0.5f ? 2.0f * x : __fdiv_rn(1.0f, __fsub_rn(2.0f, 2.0f * x)); }
+// (1/y is computed as the correctly rounded reciprocal __frcp_rn(y) == __fdiv_rn(1, y), without the generic division sequence)
+__device__ __forceinline__ float spacing(float x) { return x < 1.0f ? x * 0.5f : __fsub_rn(1.0f, __frcp_rn(2.0f * x)); }
+__device__ __forceinline__ float spacing_inv(float x) { return x < 0.5f ? 2.0f * x : __frcp_rn(__fsub_rn(2.0f, 2.0f * x)); }
 
 // real_bins = spacing_fn_inv(s_near * (1 - bins) + s_far * bins)   (renderer.py:277), unfused like torch
 __device__ __forceinline__ float real_bin(float b, float s_near, float s_far) {
@@ -116,7 +117,7 @@ __device__ __forceinline__ void contract3(float& x, float& y, float& z) {
     if (ay > mag) { mag = ay; idx = 1; }
     if (az > mag) { mag = az; idx = 2; }
     if (mag < 1.0f) return;
-    const float inv = __fdiv_rn(1.0f, mag);
+    const float inv = __frcp_rn(mag);
     const float big = __fdiv_rn(__fsub_rn(2.0f, inv), mag);
     x = __fmul_rn(x, idx == 0 ? big : inv);
     y = __fmul_rn(y, idx == 1 ? big : inv);
@@ -190,6 +191,71 @@ __device__ __forceinline__ void encode_level(const GridDev& g, int l, const floa
     }
 }
 
+// ---- software-pipelined C=2 gathers ------------------------------------------------------------------------------------
+// A level is split into `issue` (cell lookup + the 8 row loads) and `finish` (trilinear blend, same FMA order as
+// encode_level / the reference kernel); gather_levels keeps DEPTH levels of loads in flight per thread so the L1/L2
+// latency of one level hides behind the index arithmetic and the loads of the next ones.
+struct LevelLoads {
+    float2 v[8];
+    float f[3];
+};
+
+__device__ __forceinline__ void level_issue(const GridDev& g, int l, const float (&x)[3], LevelLoads& o) {
+    const uint32_t res = g.res[l];
+    const uint32_t hmask = g.hmask[l];
+    const float2* __restrict__ rows = reinterpret_cast<const float2*>(g.emb) + g.off[l];
+    const float resf = (float)res, top = (float)(res - 1);
+    uint32_t b0[3], b1[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        float pos = fminf(fmaxf(__fmaf_rn(x[d], resf, -0.5f), 0.0f), top);
+        const float fl = floorf(pos);
+        b0[d] = (uint32_t)fl;
+        b1[d] = min(b0[d] + 1, res - 1);
+        o.f[d] = pos - fl;
+    }
+    if (hmask == 0) {  // dense level: x + y*res + z*res^2 < rows, no modulo needed
+        const uint32_t y0 = b0[1] * res, y1 = b1[1] * res, z0 = b0[2] * res * res, z1 = b1[2] * res * res;
+#pragma unroll
+        for (int i = 0; i < 8; i++) o.v[i] = __ldg(rows + (((i & 1) ? b1[0] : b0[0]) + ((i & 2) ? y1 : y0) + ((i & 4) ? z1 : z0)));
+    } else {
+        const uint32_t y0 = b0[1] * 2654435761u, y1 = b1[1] * 2654435761u, z0 = b0[2] * 805459861u, z1 = b1[2] * 805459861u;
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            o.v[i] = __ldg(rows + ((((i & 1) ? b1[0] : b0[0]) ^ ((i & 2) ? y1 : y0) ^ ((i & 4) ? z1 : z0)) & hmask));
+    }
+}
+
+__device__ __forceinline__ void level_finish(const LevelLoads& o, float& o0, float& o1) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float ww = (i & 1) ? o.f[0] : 1 - o.f[0];
+        ww *= (i & 2) ? o.f[1] : 1 - o.f[1];
+        ww *= (i & 4) ? o.f[2] : 1 - o.f[2];
+        a0 = __fmaf_rn(ww, o.v[i].x, a0);
+        a1 = __fmaf_rn(ww, o.v[i].y, a1);
+    }
+    o0 = a0;
+    o1 = a1;
+}
+
+// feat[2l], feat[2l+1] = level l of grid g at x (in [0,1]^3); zeros when the point is outside (gridencoder.cu:105-130)
+template <int L, int DEPTH>
+__device__ __forceinline__ void gather_levels(const GridDev& g, const float (&x)[3], bool inside, float (&feat)[2 * L]) {
+    LevelLoads buf[DEPTH];
+#pragma unroll
+    for (int d = 0; d < DEPTH && d < L; d++) level_issue(g, d, x, buf[d]);
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+        float o0, o1;
+        level_finish(buf[l % DEPTH], o0, o1);
+        if (l + DEPTH < L) level_issue(g, l + DEPTH, x, buf[l % DEPTH]);
+        feat[2 * l] = inside ? o0 : 0.f;
+        feat[2 * l + 1] = inside ? o1 : 0.f;
+    }
+}
+
 // y[n] = sum_k W[n][k] x[k], W in shared memory as [N][KP] (KP = K rounded up to 4, zero padded);
 // every lane reads the same address (broadcast LDS.128), activations stay in registers.
 template <int K, int KP, int N, bool RELU>
@@ -212,12 +278,12 @@ __device__ __forceinline__ void dense(const float* __restrict__ W, const float (
 // ---- shared memory plan ---------------------------------------------------------------------
 template <int PL, int GL, int HG>
 struct Smem {
-    static constexpr int PK = 2 * PL, PKP = (PK + 3) & ~3;  // proposal MLP input width (padded)
+    static constexpr int PK = 2 * PL, PKP = (PK + 7) & ~7;  // proposal MLP input width (padded to the MMA K step)
     static constexpr int GK = 2 * GL;                        // grid MLP input width (multiple of 4 for GL even)
     static constexpr int VP = 33;                            // view MLP row pitch (bank-conflict free)
     // offsets in floats
-    static constexpr int prop_w0 = 0;                        // [2][16][PKP]
-    static constexpr int prop_w1 = prop_w0 + 2 * 16 * PKP;   // [2][16]
+    static constexpr int prop_w0 = 0;                        // [2 nets][hi, lo][16 x PKP operand image]
+    static constexpr int prop_w1 = prop_w0 + 4 * 16 * PKP;   // [2][16]
     // grid_mlp weights as tensor-core operand images (tc.cuh: K-major core matrices), tf32 hi part then lo part
     static constexpr int grid_w0 = (prop_w1 + 2 * 16 + 31) & ~31;  // 2 x [HG][GK]   (128-byte aligned)
     static constexpr int grid_w1 = grid_w0 + 2 * HG * GK;          // 2 x [HG][HG]
@@ -240,10 +306,9 @@ template <int PL, int GL, int HG, int HV>
 __device__ void stage_weights(float* sm, const RenderParams& p) {
     using S = Smem<PL, GL, HG>;
     const int tid = threadIdx.x;
-    for (int i = tid; i < 2 * 16 * S::PKP; i += kThreads) {
-        const int e = i / (16 * S::PKP), r = (i / S::PKP) % 16, k = i % S::PKP;
-        sm[S::prop_w0 + i] = k < S::PK ? __ldg(p.prop_w0[e] + r * S::PK + k) : 0.f;
-    }
+    for (int e = 0; e < 2; e++)
+        tc::stage_split_weights<16, S::PK, S::PKP>(sm + S::prop_w0 + e * 2 * 16 * S::PKP, sm + S::prop_w0 + (e * 2 + 1) * 16 * S::PKP,
+                                                   p.prop_w0[e], tid, kThreads);
     for (int i = tid; i < 32; i += kThreads) sm[S::prop_w1 + i] = __ldg(p.prop_w1[i / 16] + (i % 16));
     tc::stage_split_weights<HG, S::GK, S::GK>(sm + S::grid_w0, sm + S::grid_w0 + HG * S::GK, p.grid_w[0], tid, kThreads);
     tc::stage_split_weights<HG, HG, HG>(sm + S::grid_w1, sm + S::grid_w1 + HG * HG, p.grid_w[1], tid, kThreads);
@@ -348,6 +413,7 @@ __device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {
 // sample position for bins (b0,b1): midpoint t, delta, contracted point mapped to [0,1]^3
 struct RayCtx {
     float ox, oy, oz, dx, dy, dz, s_near, s_far, bound;
+    float inv_den;   // 1/(2*bound) when 2*bound is a power of two (then x/den == x*inv_den exactly), else 0
     bool contract;
 };
 
@@ -360,9 +426,15 @@ __device__ __forceinline__ bool sample_point(const RayCtx& r, float b0, float b1
     float z = __fadd_rn(r.oz, __fmul_rn(r.dz, tmid));
     if (r.contract) contract3(x, y, z);
     const float den = 2.0f * r.bound;                       // grid.py:156
-    x01[0] = __fdiv_rn(__fadd_rn(x, r.bound), den);
-    x01[1] = __fdiv_rn(__fadd_rn(y, r.bound), den);
-    x01[2] = __fdiv_rn(__fadd_rn(z, r.bound), den);
+    if (r.inv_den != 0.f) {
+        x01[0] = __fmul_rn(__fadd_rn(x, r.bound), r.inv_den);
+        x01[1] = __fmul_rn(__fadd_rn(y, r.bound), r.inv_den);
+        x01[2] = __fmul_rn(__fadd_rn(z, r.bound), r.inv_den);
+    } else {
+        x01[0] = __fdiv_rn(__fadd_rn(x, r.bound), den);
+        x01[1] = __fdiv_rn(__fadd_rn(y, r.bound), den);
+        x01[2] = __fdiv_rn(__fadd_rn(z, r.bound), den);
+    }
     bool oob = false;                                       // gridencoder.cu:105-111 -> zeros
 #pragma unroll
     for (int d = 0; d < 3; d++) oob |= (x01[d] < 0.f || x01[d] > 1.f);
@@ -371,32 +443,27 @@ __device__ __forceinline__ bool sample_point(const RayCtx& r, float b0, float b1
 
 // proposal stage: T samples through proposal network e; fills ds[] with delta*sigma
 template <int T, int PL, int GL, int HG>
-__device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, const float* sm, const RayCtx& r, const float* bins, float* ds,
-                                               int lane) {
+__device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, const float* sm, tc::Group& grp, const RayCtx& r,
+                                               const float* bins, float* ds, int lane) {
     using S = Smem<PL, GL, HG>;
     const GridDev& g = p.prop[e];
-    const float* w0 = sm + S::prop_w0 + e * 16 * S::PKP;
+    const float* w0 = sm + S::prop_w0 + e * 2 * 16 * S::PKP;  // hi image; lo image follows
     const float* w1 = sm + S::prop_w1 + e * 16;
 #pragma unroll 1
     for (int i = 0; i < T / 32; i++) {
         const int j = lane + 32 * i;
         float tmid, delta, x01[3];
         const bool inside = sample_point(r, bins[j], bins[j + 1], tmid, delta, x01);
-        float feat[2 * PL];
-        if (inside) {
+        float feat[S::PKP];
+        {
+            float f[2 * PL];
+            gather_levels<PL, 3>(g, x01, inside, f);
 #pragma unroll
-            for (int l = 0; l < PL; l++) {
-                float o[2];
-                encode_level<2>(g, l, x01, o);
-                feat[2 * l] = o[0];
-                feat[2 * l + 1] = o[1];
-            }
-        } else {
-#pragma unroll
-            for (int k = 0; k < 2 * PL; k++) feat[k] = 0.f;
+            for (int k = 0; k < S::PKP; k++) feat[k] = k < 2 * PL ? f[k] : 0.f;
         }
+        // prop_mlp layer 0 (2L -> 16, ReLU; network.py:137,142) on the tensor core: 4 warps x 32 samples = one 128-row MMA tile
         float h[16];
-        dense<2 * PL, S::PKP, 16, true>(w0, feat, h);
+        tc::group_layer<S::PKP, 16, true>(grp, w0, w0 + 16 * S::PKP, feat, h);
         float o = 0.f;
 #pragma unroll
         for (int k = 0; k < 16; k += 4) {
@@ -448,6 +515,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         r.ox = __ldg(p.rays_o + 3 * (size_t)ray); r.oy = __ldg(p.rays_o + 3 * (size_t)ray + 1); r.oz = __ldg(p.rays_o + 3 * (size_t)ray + 2);
         r.dx = __ldg(p.rays_d + 3 * (size_t)ray); r.dy = __ldg(p.rays_d + 3 * (size_t)ray + 1); r.dz = __ldg(p.rays_d + 3 * (size_t)ray + 2);
         r.bound = p.bound;
+        {
+            const float den = 2.0f * p.bound;
+            const bool pow2 = (__float_as_uint(den) & 0x007fffffu) == 0 && den >= 1.0f / 1024 && den <= 1048576.0f;
+            r.inv_den = pow2 ? __frcp_rn(den) : 0.f;
+        }
         r.contract = p.contract != 0;
         float near = -CUDART_INF_F, far = CUDART_INF_F;
         {
@@ -474,13 +546,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         // ---- stage 0: uniform bins linspace(0,1,129) (renderer.py:262-266; i/128 is exact) ------
         for (int j = lane; j <= kMaxT; j += 32) binsA[j] = (float)j * (1.0f / kMaxT);
         __syncwarp();
-        proposal_stage<128, PL, GL, HG>(p, 0, sm, r, binsA, ds, lane);
+        proposal_stage<128, PL, GL, HG>(p, 0, sm, grp, r, binsA, ds, lane);
         weights_from_ds<128>(ds, lane, last_opaque);
         __syncwarp();
         sample_pdf_warp<128, 65>(ds, binsA, cdf, u65, binsB, lane, (p.inds0 && active) ? p.inds0 + 65 * (size_t)ray : nullptr);
 
         // ---- stage 1 -----------------------------------------------------------------------------
-        proposal_stage<64, PL, GL, HG>(p, 1, sm, r, binsB, ds, lane);
+        proposal_stage<64, PL, GL, HG>(p, 1, sm, grp, r, binsB, ds, lane);
         weights_from_ds<64>(ds, lane, last_opaque);
         __syncwarp();
         sample_pdf_warp<64, 33>(ds, binsB, cdf, u33, binsA, lane, (p.inds1 && active) ? p.inds1 + 33 * (size_t)ray : nullptr);
@@ -491,18 +563,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         float f16[16];  // grid_mlp output: [0] log-density, [1..15] geo_feat
         {
             float feat[2 * GL];
-            if (inside) {
-#pragma unroll
-                for (int l = 0; l < GL; l++) {
-                    float o[2];
-                    encode_level<2>(p.grid, l, x01, o);
-                    feat[2 * l] = o[0];
-                    feat[2 * l + 1] = o[1];
-                }
-            } else {
-#pragma unroll
-                for (int k = 0; k < 2 * GL; k++) feat[k] = 0.f;
-            }
+            gather_levels<GL, 2>(p.grid, x01, inside, feat);
             // grid_mlp 2L -> Hg -> Hg -> 16 (ReLU, no bias; network.py:94) on the tensor core: the 4 warps of the group put
             // their 4 x 32 samples into the 128 TMEM lanes, tcgen05.mma (3xTF32 split precision) does the three layers
             float h1[HG];
@@ -556,7 +617,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             const float o = warp_sum(sm[S::view_w2 + c * 32 + lane] * h2);
-            const float s = __fdiv_rn(1.0f, 1.0f + expf(-o));                       // sigmoid
+            const float s = __frcp_rn(1.0f + expf(-o));                             // sigmoid
             const float bg = p.bg ? __ldg(p.bg + (p.bg_rows > 1 ? 3 * (size_t)ray : 0) + c) : p.bg_scalar;
             rgb[c] = __fadd_rn(s, __fmul_rn(__fsub_rn(1.0f, wsum), bg));            // renderer.py:353
         }
