@@ -209,17 +209,16 @@ def main():
     host_rays = [tuple(t.pin_memory() for t in get_rays(poses[k], intr, H * world, W, rows=rows)) for k in range(n_res)]
     dev_rays = [(o.to(dev), d.to(dev)) for o, d in host_rays]
     kw = {}
-    sam_rows = 5
     if wl == "mask":
         kw = dict(return_mask=1)
 
     def render_frame(ro, rd):
         if wl == "sam":
-            # staged + return_feats is impossible in the reference API: feature frames are rendered
-            # as one non-staged call per `sam_rows` image rows and concatenated
-            parts = [model.render(ro[h0 * W:(h0 + sam_rows) * W], rd[h0 * W:(h0 + sam_rows) * W], staged=False, perturb=False,
-                                  return_feats=1, H=sam_rows, W=W) for h0 in range(0, H, sam_rows)]
-            out = {k: torch.cat([p[k].reshape(-1, *p[k].shape[2:]) if k == "samvit" else p[k] for p in parts]) for k in keys}
+            # staged + return_feats is impossible in the reference API (`samvit.view(H, W, -1)` on a chunk),
+            # so the feature frame is ONE non-staged call over all H*W rays with H, W of this rank's block -- the reference's own
+            # call shape (trainer.py:536-537), which it can only afford at 64x64 because it materialises [N,32,128] tensors
+            out = model.render(ro, rd, staged=False, perturb=False, return_feats=1, H=H, W=W)
+            out = {k: (out[k].reshape(-1, out[k].shape[-1]) if k == "samvit" else out[k]) for k in keys}
         else:
             out = model.render(ro, rd, staged=True, perturb=False, **kw)
         if world > 1:

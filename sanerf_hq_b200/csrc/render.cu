@@ -559,7 +559,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 
         // ---- stage 2: the radiance field, one sample per lane -----------------------------------
         float tmid, delta, x01[3];
-        const bool inside = sample_point(r, binsA[lane], binsA[lane + 1], tmid, delta, x01);
+        const int home = lane;   // the sample this lane owns in the final stage
+        const bool inside = sample_point(r, binsA[home], binsA[home + 1], tmid, delta, x01);
         float f16[16];  // grid_mlp output: [0] log-density, [1..15] geo_feat
         {
             float feat[2 * GL];
@@ -573,11 +574,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             tc::group_layer<HG, 16, false>(grp, sm + S::grid_w2, sm + S::grid_w2 + 16 * HG, h2, f16);
         }
         const float sigma = expf(f16[0]);
-        ds[lane] = __fmul_rn(delta, sigma);
+        ds[home] = __fmul_rn(delta, sigma);
         __syncwarp();
         weights_from_ds<32>(ds, lane, last_opaque);
         __syncwarp();
-        const float w = ds[lane];
+        const float w = ds[home];
         __syncwarp();
 
         // ---- composite (renderer.py:333-340, 353) ------------------------------------------------
@@ -628,8 +629,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         }
 
         // ---- parity taps ------------------------------------------------------------------------
-        if (p.weights2 && active) p.weights2[32 * (size_t)ray + lane] = w;
-        if (p.sigma2 && active) p.sigma2[32 * (size_t)ray + lane] = sigma;
+        if (p.weights2 && active) p.weights2[32 * (size_t)ray + home] = w;
+        if (p.sigma2 && active) p.sigma2[32 * (size_t)ray + home] = sigma;
         if (p.bins2 && active) {
             p.bins2[33 * (size_t)ray + lane] = binsA[lane];
             if (lane == 0) p.bins2[33 * (size_t)ray + 32] = binsA[32];
@@ -675,7 +676,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         // ---- object head input: per-sample cat[m_grid(x), geo_feat] (renderer.py:304-305, 378) ---
         if constexpr (MASK) if (active) {
             const int nl = (int)p.mgrid.L;
-            float* dst = p.mask_in + ((size_t)ray * 32 + lane) * (8 * nl + 15);
+            float* dst = p.mask_in + ((size_t)ray * 32 + home) * (8 * nl + 15);
 #pragma unroll 1
             for (int l = 0; l < nl; l++) {
                 float o[8];
