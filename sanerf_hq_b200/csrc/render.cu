@@ -41,6 +41,9 @@ struct GridDev {
     uint32_t off[SANERF_MAX_LEVELS];    // row offset of the level
     uint32_t res[SANERF_MAX_LEVELS];    // kernel-side resolution
     uint32_t hmask[SANERF_MAX_LEVELS];  // rows-1 for hashed levels (rows is a power of two), 0 = dense
+    const void* base[SANERF_MAX_LEVELS];  // emb + off[l]*C: first row of the level (saves the per-load offset add)
+    float resf[SANERF_MAX_LEVELS];        // (float)res, (float)(res-1)
+    float topf[SANERF_MAX_LEVELS];
 };
 
 struct RenderParams {
@@ -203,8 +206,8 @@ struct LevelLoads {
 __device__ __forceinline__ void level_issue(const GridDev& g, int l, const float (&x)[3], LevelLoads& o) {
     const uint32_t res = g.res[l];
     const uint32_t hmask = g.hmask[l];
-    const float2* __restrict__ rows = reinterpret_cast<const float2*>(g.emb) + g.off[l];
-    const float resf = (float)res, top = (float)(res - 1);
+    const float2* __restrict__ rows = reinterpret_cast<const float2*>(g.base[l]);
+    const float resf = g.resf[l], top = g.topf[l];
     uint32_t b0[3], b1[3];
 #pragma unroll
     for (int d = 0; d < 3; d++) {
@@ -219,10 +222,12 @@ __device__ __forceinline__ void level_issue(const GridDev& g, int l, const float
 #pragma unroll
         for (int i = 0; i < 8; i++) o.v[i] = __ldg(rows + (((i & 1) ? b1[0] : b0[0]) + ((i & 2) ? y1 : y0) + ((i & 4) ? z1 : z0)));
     } else {
-        const uint32_t y0 = b0[1] * 2654435761u, y1 = b1[1] * 2654435761u, z0 = b0[2] * 805459861u, z1 = b1[2] * 805459861u;
+        // (x ^ y*P1 ^ z*P2) & mask == (x & mask) ^ (y*P1 & mask) ^ (z*P2 & mask): 6 ANDs + 8 three-input XORs
+        const uint32_t x0 = b0[0] & hmask, x1 = b1[0] & hmask;
+        const uint32_t y0 = (b0[1] * 2654435761u) & hmask, y1 = (b1[1] * 2654435761u) & hmask;
+        const uint32_t z0 = (b0[2] * 805459861u) & hmask, z1 = (b1[2] * 805459861u) & hmask;
 #pragma unroll
-        for (int i = 0; i < 8; i++)
-            o.v[i] = __ldg(rows + ((((i & 1) ? b1[0] : b0[0]) ^ ((i & 2) ? y1 : y0) ^ ((i & 4) ? z1 : z0)) & hmask));
+        for (int i = 0; i < 8; i++) o.v[i] = __ldg(rows + (((i & 1) ? x1 : x0) ^ ((i & 2) ? y1 : y0) ^ ((i & 4) ? z1 : z0)));
     }
 }
 
@@ -253,6 +258,30 @@ __device__ __forceinline__ void gather_levels(const GridDev& g, const float (&x)
         if (l + DEPTH < L) level_issue(g, l + DEPTH, x, buf[l % DEPTH]);
         feat[2 * l] = inside ? o0 : 0.f;
         feat[2 * l + 1] = inside ? o1 : 0.f;
+    }
+}
+
+// two points at once (two sample chunks of the same ray): twice the independent loads in flight per thread
+template <int L, int DEPTH>
+__device__ __forceinline__ void gather_levels_x2(const GridDev& g, const float (&xa)[3], const float (&xb)[3], bool ina, bool inb,
+                                                 float (&fa)[2 * L], float (&fb)[2 * L]) {
+    LevelLoads bufa[DEPTH], bufb[DEPTH];
+#pragma unroll
+    for (int d = 0; d < DEPTH && d < L; d++) {
+        level_issue(g, d, xa, bufa[d]);
+        level_issue(g, d, xb, bufb[d]);
+    }
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+        float a0, a1, b0, b1;
+        level_finish(bufa[l % DEPTH], a0, a1);
+        if (l + DEPTH < L) level_issue(g, l + DEPTH, xa, bufa[l % DEPTH]);
+        level_finish(bufb[l % DEPTH], b0, b1);
+        if (l + DEPTH < L) level_issue(g, l + DEPTH, xb, bufb[l % DEPTH]);
+        fa[2 * l] = ina ? a0 : 0.f;
+        fa[2 * l + 1] = ina ? a1 : 0.f;
+        fb[2 * l] = inb ? b0 : 0.f;
+        fb[2 * l + 1] = inb ? b1 : 0.f;
     }
 }
 
@@ -449,29 +478,37 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, con
     const GridDev& g = p.prop[e];
     const float* w0 = sm + S::prop_w0 + e * 2 * 16 * S::PKP;  // hi image; lo image follows
     const float* w1 = sm + S::prop_w1 + e * 16;
+    // two chunks of 32 samples per iteration: twice the gather loads in flight, and ONE tensor-core round for both
 #pragma unroll 1
-    for (int i = 0; i < T / 32; i++) {
-        const int j = lane + 32 * i;
-        float tmid, delta, x01[3];
-        const bool inside = sample_point(r, bins[j], bins[j + 1], tmid, delta, x01);
-        float feat[S::PKP];
+    for (int i = 0; i < T / 64; i++) {
+        const int ja = lane + 64 * i, jb = ja + 32;
+        float tmid, da, db, xa[3], xb[3];
+        const bool ina = sample_point(r, bins[ja], bins[ja + 1], tmid, da, xa);
+        const bool inb = sample_point(r, bins[jb], bins[jb + 1], tmid, db, xb);
+        float feata[S::PKP], featb[S::PKP];
         {
-            float f[2 * PL];
-            gather_levels<PL, 3>(g, x01, inside, f);
+            float fa[2 * PL], fb[2 * PL];
+            gather_levels_x2<PL, 2>(g, xa, xb, ina, inb, fa, fb);
 #pragma unroll
-            for (int k = 0; k < S::PKP; k++) feat[k] = k < 2 * PL ? f[k] : 0.f;
+            for (int k = 0; k < S::PKP; k++) {
+                feata[k] = k < 2 * PL ? fa[k] : 0.f;
+                featb[k] = k < 2 * PL ? fb[k] : 0.f;
+            }
         }
-        // prop_mlp layer 0 (2L -> 16, ReLU; network.py:137,142) on the tensor core: 4 warps x 32 samples = one 128-row MMA tile
-        float h[16];
-        tc::group_layer<S::PKP, 16, true>(grp, w0, w0 + 16 * S::PKP, feat, h);
-        float o = 0.f;
+        // prop_mlp layer 0 (2L -> 16, ReLU; network.py:137,142) on the tensor core: 4 warps x 32 samples = one 128-row MMA tile per chunk
+        float ha[16], hb[16];
+        tc::group_layer_x2<S::PKP, 16, true>(grp, w0, w0 + 16 * S::PKP, feata, featb, ha, hb);
+        float oa = 0.f, ob = 0.f;
 #pragma unroll
         for (int k = 0; k < 16; k += 4) {
             const float4 w = *reinterpret_cast<const float4*>(w1 + k);
-            o = __fmaf_rn(w.x, h[k], o); o = __fmaf_rn(w.y, h[k + 1], o);
-            o = __fmaf_rn(w.z, h[k + 2], o); o = __fmaf_rn(w.w, h[k + 3], o);
+            oa = __fmaf_rn(w.x, ha[k], oa); oa = __fmaf_rn(w.y, ha[k + 1], oa);
+            oa = __fmaf_rn(w.z, ha[k + 2], oa); oa = __fmaf_rn(w.w, ha[k + 3], oa);
+            ob = __fmaf_rn(w.x, hb[k], ob); ob = __fmaf_rn(w.y, hb[k + 1], ob);
+            ob = __fmaf_rn(w.z, hb[k + 2], ob); ob = __fmaf_rn(w.w, hb[k + 3], ob);
         }
-        ds[j] = __fmul_rn(delta, expf(o));                  // trunc_exp fwd (activation.py:10); renderer.py:310
+        ds[ja] = __fmul_rn(da, expf(oa));                   // trunc_exp fwd (activation.py:10); renderer.py:310
+        ds[jb] = __fmul_rn(db, expf(ob));
     }
     __syncwarp();
 }
@@ -732,6 +769,9 @@ static int fill_grid(GridDev& g, const sanerf_grid_t& s, uint32_t C_expected) {
         for (int d = 0; d < 3 && stride <= rows; d++) stride *= res;
         g.off[l] = s.offset[l];
         g.res[l] = res;
+        g.base[l] = s.embeddings + (size_t)s.offset[l] * s.level_dim;
+        g.resf[l] = (float)res;
+        g.topf[l] = (float)(res - 1);
         if (stride <= rows) {
             g.hmask[l] = 0;  // dense, index < res^3 <= rows
         } else {
@@ -739,7 +779,11 @@ static int fill_grid(GridDev& g, const sanerf_grid_t& s, uint32_t C_expected) {
             g.hmask[l] = rows - 1;
         }
     }
-    for (uint32_t l = s.num_levels; l < SANERF_MAX_LEVELS; l++) g.off[l] = g.res[l] = g.hmask[l] = 0;
+    for (uint32_t l = s.num_levels; l < SANERF_MAX_LEVELS; l++) {
+        g.off[l] = g.res[l] = g.hmask[l] = 0;
+        g.base[l] = nullptr;
+        g.resf[l] = g.topf[l] = 0.f;
+    }
     return 0;
 }
 

@@ -253,5 +253,38 @@ __device__ __forceinline__ void group_layer(Group& g, const float* s_hi, const f
     }
 }
 
+// Two independent 128-row tiles (each thread owns one row of each) through the same layer in ONE round: tile t uses A columns
+// [t*2K, (t+1)*2K) (hi | lo) and D columns [t*N, (t+1)*N).  Needs 4K <= 64 and 2N <= 64.
+template <int K, int N, bool RELU>
+__device__ __forceinline__ void group_layer_x2(Group& g, const float* s_hi, const float* s_lo, const float (&a0)[K], const float (&a1)[K],
+                                               float (&d0)[N], float (&d1)[N]) {
+    static_assert(K % 8 == 0 && 4 * K <= (int)kACols && N % 16 == 0 && 2 * N <= 64, "layer shape (two tiles)");
+    const uint32_t d_mma = g.d_mma, a_mma = g.a_mma;
+    st_split<K, 0>(g.a_rw, a0);
+    st_split<K, 1>(g.a_rw + K, a0);
+    st_split<K, 0>(g.a_rw + 2 * K, a1);
+    st_split<K, 1>(g.a_rw + 3 * K, a1);
+    group_round(g, [&] {
+#pragma unroll
+        for (int t = 0; t < 2; t++) {
+            issue_layer<N, K / 8>(d_mma + t * N, a_mma + t * 2 * K, s_hi, 0u);
+            issue_layer<N, K / 8>(d_mma + t * N, a_mma + t * 2 * K, s_lo, 1u);
+            issue_layer<N, K / 8>(d_mma + t * N, a_mma + t * 2 * K + K, s_hi, 1u);
+        }
+    });
+#pragma unroll
+    for (int c = 0; c < 2 * N; c += 16) {
+        uint32_t t[16];
+        tmem_ld16(g.d_rw + c, t);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+            const float v = __uint_as_float(t[i]);
+            if (c + i < N) d0[c + i] = RELU ? fmaxf(v, 0.f) : v;
+            else d1[c + i - N] = RELU ? fmaxf(v, 0.f) : v;
+        }
+    }
+}
+
 }  // namespace tc
 }  // namespace sanerf
