@@ -24,6 +24,7 @@
 #ifndef SANERF_B200_H
 #define SANERF_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -175,6 +176,8 @@ typedef struct {
                                        (renderer.py:361-367); requires model->s_grid */
     float *mask_in;                 /* optional [N,32, 8*Lm+15] (143): per-sample cat[m_grid(x), geo_feat], the mask_mlp
                                        input (renderer.py:304-305, 378); requires model->m_grid */
+    uint32_t mask_in_tiled;         /* 0: row-major as above; 1: tile-transposed [ceil(N*32/128)][K][128] (row = ray*32+sample),
+                                       the layout sanerf_mask_mlp consumes; N must then start at a multiple of 4 rays */
     /* optional debug / parity taps (NULL to skip) */
     int16_t *inds0;                 /* [N,65]  searchsorted result of the 1st sample_pdf */
     int16_t *inds1;                 /* [N,33]  of the 2nd */
@@ -195,6 +198,16 @@ int sanerf_render_launch_count(const sanerf_model_t *model, const sanerf_render_
  * new_bins [N,T], inds [N,T] (int16) ; T0+1 <= 129, T in {65,33} with u = the linspace table. */
 int sanerf_sample_pdf(const float *bins, const float *weights, const float *u, uint32_t N, uint32_t T0,
                       uint32_t T, float *new_bins, int16_t *inds, sanerf_stream_t stream);
+
+/* Object (instance-mask) head on the tensor cores: replaces `mask_mlp(cat[masks, geo_feat])` + the weighted sum over samples
+ * (nerf/renderer.py:376-385; SkipConnMLP 143 -> 256 -> 256 -> n_inst, no bias, leaky_relu 0.01, network.py:119-123).
+ * mask_in_tiled: tile-transposed per-sample inputs written by sanerf_render (mask_in_tiled = 1); weights [n_rays,32] = the
+ * final-stage compositing weights; w0 [256,143], w1 [256,256], w2 [n_inst,256] in nn.Linear layout; workspace: device
+ * scratch of sanerf_mask_mlp_workspace_bytes() for the split-precision operand images; logits [n_rays,n_inst].
+ * bf16 hi/lo split operands, fp32 accumulation (error ~1e-5 relative).  n_inst <= 16. */
+size_t sanerf_mask_mlp_workspace_bytes(void);
+int sanerf_mask_mlp(const float *mask_in_tiled, const float *weights, const float *w0, const float *w1, const float *w2,
+                    uint32_t n_inst, uint32_t n_rays, void *workspace, float *logits, sanerf_stream_t stream);
 
 /* Validation entry point for the tcgen05 (5th-gen tensor core) MLP path that the fused render uses for grid_mlp
  * (nerf/network.py:9-29 `MLP`, bias-free, ReLU between layers): out[M,16] = relu(relu(x W0^T) W1^T) W2^T with

@@ -33,7 +33,7 @@ class RenderArgsT(ctypes.Structure):
     _fields_ = [("rays_o", _vp), ("rays_d", _vp), ("N", _u32), ("cam_near_far", _vp), ("cam_near_far_rows", _u32),
                 ("bg_color", _vp), ("bg_rows", _u32), ("bg_scalar", _f32),
                 ("image", _vp), ("depth", _vp), ("weights_sum", _vp), ("sam_in", _vp), ("mask_in", _vp),
-                ("inds0", _vp), ("inds1", _vp), ("weights2", _vp), ("sigma2", _vp), ("bins2", _vp), ("f_image", _vp)]
+                ("mask_in_tiled", _u32), ("inds0", _vp), ("inds1", _vp), ("weights2", _vp), ("sigma2", _vp), ("bins2", _vp), ("f_image", _vp)]
 
 
 # name -> argtypes (restype is int for all but the two noted)
@@ -53,6 +53,8 @@ PROTOTYPES = {
     "sanerf_render_launch_count": [ctypes.POINTER(ModelT), ctypes.POINTER(RenderArgsT)],
     "sanerf_sample_pdf": [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp],
     "sanerf_mlp3_tc": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp],
+    "sanerf_mask_mlp_workspace_bytes": [],
+    "sanerf_mask_mlp": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp],
     "sanerf_abi_version": [],
     "sanerf_error_string": [_i32],
 }
@@ -85,7 +87,8 @@ def load():
             raise RuntimeError(f"{path} does not export {name}; rebuild the library")
         fn = getattr(L, name)
         fn.argtypes = argtypes
-        fn.restype = ctypes.c_char_p if name == "sanerf_error_string" else ctypes.c_int
+        fn.restype = (ctypes.c_char_p if name == "sanerf_error_string" else
+                      ctypes.c_size_t if name == "sanerf_mask_mlp_workspace_bytes" else ctypes.c_int)
     _lib = L
     return L
 

@@ -1,0 +1,301 @@
+// heads.cu -- the object (instance-mask) head of the render path on the 5th-gen tensor cores (sm_100a).
+//
+// Reference: nerf/renderer.py:376-385 + nerf/network.py:119-123, 31-66 (SkipConnMLP, no skip, no bias, leaky_relu 0.01):
+//     point_masks = mask_mlp(cat[m_grid(x) (128), geo_feat (15)])         per SAMPLE, 143 -> 256 -> 256 -> n_inst
+//     instance_mask_logits = sum_samples weights * point_masks             per ray
+// 6.57 MFLOP per ray, 4.2 TFLOP per 800x800 frame: the one dense contraction of the path.
+//
+// One CTA (8 warps) owns the tensor memory of its SM and walks over tiles of 128 samples (= 4 rays):
+//   * activations live in TMEM as the A operand (bf16 hi | bf16 lo, two K values per 32-bit column), one row per TMEM lane;
+//     warps w and w+4 share the 32 lanes of sub-partition w and split the columns between them;
+//   * weights are pre-split into bf16 hi / lo operand images (K-major, no swizzle) by a prepare kernel and streamed from L2
+//     through a double-buffered cp.async ring of K-chunks (the whole MLP is 410 KB of operands -- it does not fit in smem);
+//   * D[128,256] fp32 accumulates in TMEM columns [256,512); the epilogue of a layer reads D, applies leaky_relu, splits to
+//     bf16 hi/lo and writes the next layer's A operand straight back to TMEM columns [0,256);
+//   * split precision: D = Ah*Wh + Ah*Wl + Al*Wh (the dropped Al*Wl is 2^-18 relative), fp32 accumulation;
+//   * the last layer (N padded to 16) is composited with the sample weights by a warp reduction (one warp = one ray).
+//
+// Input layout: the render kernel writes the per-sample inputs "tile-transposed", [tile][k][128 rows], so that both its stores
+// and the loads here are coalesced (row r = ray*32 + sample; tile = r / 128).
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "tc.cuh"
+
+namespace sanerf {
+
+constexpr int kHeadThreads = 256;
+constexpr int kMaskK0 = 143, kMaskK0P = 144, kMaskH = 256, kMaskNOut = 16;
+constexpr int kCh0 = 48, kNCh0 = 3;   // layer 0: 144 = 3 chunks of 48
+constexpr int kCh1 = 64, kNCh1 = 4;   // layer 1: 256 = 4 chunks of 64
+constexpr int kChunksPerTile = kNCh0 + kNCh1;
+// operand-image sizes in bf16 elements (hi image followed by lo image)
+constexpr int kImg0 = 2 * kMaskH * kCh0, kImg1 = 2 * kMaskH * kCh1, kImg2 = 2 * kMaskNOut * kMaskH;
+constexpr int kOff1 = kNCh0 * kImg0, kOff2 = kOff1 + kNCh1 * kImg1, kImgTotal = kOff2 + kImg2;
+constexpr int kStageBytes = kImg1 * 2;  // 65536
+constexpr uint32_t kColsAlo = 128, kColsD = 256;
+
+// element index (bf16 units) inside an [N x Kc] K-major no-swizzle operand image: core matrix = 8 n x 8 k (16 B per row)
+__host__ __device__ constexpr int img_index(int n, int k, int N) { return ((k >> 3) * N + n) * 8 + (k & 7); }
+
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+
+// ---- prepare: nn.Linear weights -> chunked operand images -------------------------------------------------------
+__global__ void mask_prepare_kernel(const float* __restrict__ w0, const float* __restrict__ w1, const float* __restrict__ w2, uint32_t n_inst,
+                                    __nv_bfloat16* __restrict__ img) {
+    const int stride = gridDim.x * blockDim.x;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kMaskH * kMaskK0P; i += stride) {   // layer 0 [256,143(+1)]
+        const int n = i / kMaskK0P, k = i % kMaskK0P, c = k / kCh0, kk = k % kCh0;
+        __nv_bfloat16 h, l;
+        split_bf16(k < kMaskK0 ? w0[n * kMaskK0 + k] : 0.f, h, l);
+        img[c * kImg0 + img_index(n, kk, kMaskH)] = h;
+        img[c * kImg0 + kMaskH * kCh0 + img_index(n, kk, kMaskH)] = l;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kMaskH * kMaskH; i += stride) {     // layer 1 [256,256]
+        const int n = i / kMaskH, k = i % kMaskH, c = k / kCh1, kk = k % kCh1;
+        __nv_bfloat16 h, l;
+        split_bf16(w1[n * kMaskH + k], h, l);
+        img[kOff1 + c * kImg1 + img_index(n, kk, kMaskH)] = h;
+        img[kOff1 + c * kImg1 + kMaskH * kCh1 + img_index(n, kk, kMaskH)] = l;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kMaskNOut * kMaskH; i += stride) {  // layer 2 [n_inst,256] -> 16 rows
+        const int n = i / kMaskH, k = i % kMaskH;
+        __nv_bfloat16 h, l;
+        split_bf16(n < (int)n_inst ? w2[n * kMaskH + k] : 0.f, h, l);
+        img[kOff2 + img_index(n, k, kMaskNOut)] = h;
+        img[kOff2 + kMaskNOut * kMaskH + img_index(n, k, kMaskNOut)] = l;
+    }
+}
+
+// ---- tensor-core helpers (kind::f16, bf16 operands, A from TMEM) -----------------------------------------------------
+__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// one K-chunk of a layer: for every 16-wide k-step the three split-precision products
+//   a_col: first A column of the chunk (hi part; the lo part sits kColsAlo columns further)
+template <int N, int KC>
+__device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_col, uint32_t img_saddr, uint32_t first_accumulate) {
+    constexpr uint32_t idesc = idesc_bf16(128, N);
+    constexpr uint32_t kstep_bytes = 2 * N * 16, lo_off = N * KC * 2;
+#pragma unroll
+    for (int j = 0; j < KC / 16; j++) {
+        const uint64_t bh = tc::smem_desc_kmajor(img_saddr + j * kstep_bytes, N * 16, 128);
+        const uint64_t bl = tc::smem_desc_kmajor(img_saddr + lo_off + j * kstep_bytes, N * 16, 128);
+        mma_bf16_ts(d_tmem, a_col + 8 * j, bh, idesc, (j > 0) ? 1u : first_accumulate);
+        mma_bf16_ts(d_tmem, a_col + 8 * j, bl, idesc, 1u);
+        mma_bf16_ts(d_tmem, a_col + kColsAlo + 8 * j, bh, idesc, 1u);
+    }
+}
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// 16 fp32 activations -> 8 columns of bf16 hi pairs + 8 columns of bf16 lo pairs (k even in the low half)
+__device__ __forceinline__ void pack_split16(const float (&v)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v[2 * i], h0, l0);
+        split_bf16(v[2 * i + 1], h1, l1);
+        hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+}
+
+__global__ void __launch_bounds__(kHeadThreads, 1)
+    mask_mlp_kernel(const float* __restrict__ mask_in, const float* __restrict__ weights, const __nv_bfloat16* __restrict__ img,
+                    float* __restrict__ logits, uint32_t n_tiles, uint32_t n_rays, uint32_t n_inst) {
+    extern __shared__ __align__(128) uint8_t smem[];   // [2 stages x 64 KB][layer-2 image 16 KB]
+    __shared__ __align__(8) uint64_t bar_free[2], bar_done;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, part = warp >> 2;
+    const uint32_t stage_saddr = tc::smem_u32(smem), w2_saddr = stage_saddr + 2 * kStageBytes;
+
+    // resident layer-2 image + barriers + tensor memory
+    for (int i = tid; i < kImg2 * 2 / 16; i += kHeadThreads) cp_async16(w2_saddr + i * 16, reinterpret_cast<const uint8_t*>(img + kOff2) + i * 16);
+    cp_async_commit();
+    if (tid == 0) {
+        tc::mbar_init(&bar_free[0], 1);
+        tc::mbar_init(&bar_free[1], 1);
+        tc::mbar_init(&bar_done, 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tm = tmem_base_s;
+    const uint32_t a_mma = tm, d_mma = tm + kColsD;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t a_rw = a_mma + lane_base, d_rw = d_mma + lane_base;
+    uint32_t ph_free[2] = {0, 0}, ph_done = 0;
+
+    const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t total_chunks = my_tiles * kChunksPerTile;
+    // chunk g of this CTA's stream -> source image and byte count (the images are the same for every tile)
+    auto load_chunk = [&](uint32_t g) {
+        const uint32_t c = g % kChunksPerTile;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(c < kNCh0 ? img + c * kImg0 : img + kOff1 + (c - kNCh0) * kImg1);
+        const uint32_t bytes = (c < kNCh0 ? kImg0 : kImg1) * 2, dst = stage_saddr + (g & 1) * kStageBytes;
+        for (uint32_t i = tid; i < bytes / 16; i += kHeadThreads) cp_async16(dst + i * 16, src + i * 16);
+        cp_async_commit();
+    };
+    // a chunk is consumed: its MMAs are issued; then the stage the PREVIOUS chunk used is recycled for the NEXT chunk
+    uint32_t g = 0;
+    auto consume = [&](auto&& issue, bool last_of_layer) {
+        cp_async_wait_all();              // chunk g (and, the first time, the layer-2 image) has landed
+        tc::fence_proxy_async_smem();     // cp.async wrote through the generic proxy; the tensor core reads through the async proxy
+        tc::fence_before_sync();          // this thread's tcgen05.st / tcgen05.ld are ordered before the barrier
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            issue(stage_saddr + (g & 1) * kStageBytes);
+            tc::mma_commit(&bar_free[g & 1]);
+            if (last_of_layer) tc::mma_commit(&bar_done);
+        }
+        __syncwarp();
+        if (g + 1 < total_chunks) {
+            if (g >= 1) {                 // MMAs of chunk g-1 read stage (g+1)&1
+                tc::mbar_wait(&bar_free[(g + 1) & 1], ph_free[(g + 1) & 1]);
+                ph_free[(g + 1) & 1] ^= 1;
+            }
+            load_chunk(g + 1);
+        }
+        g++;
+    };
+    auto wait_layer = [&] {
+        tc::mbar_wait(&bar_done, ph_done);
+        ph_done ^= 1;
+        tc::fence_after_sync();
+    };
+    // D[:, part*128 .. +128) -> leaky_relu -> bf16 hi/lo -> A columns of the next layer
+    auto epilogue_to_a = [&] {
+#pragma unroll 1
+        for (int grp = 0; grp < 8; grp++) {
+            uint32_t t[16];
+            tc::tmem_ld16(d_rw + part * 128 + grp * 16, t);
+            tc::tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const float x = __uint_as_float(t[i]);
+                v[i] = x > 0.f ? x : 0.01f * x;   // F.leaky_relu default slope (network.py:66)
+            }
+            uint32_t hi[8], lo[8];
+            pack_split16(v, hi, lo);
+            tc::tmem_st8(a_rw + part * 64 + grp * 8, hi);
+            tc::tmem_st8(a_rw + kColsAlo + part * 64 + grp * 8, lo);
+        }
+        tc::tmem_st_wait();
+    };
+
+    if (total_chunks) load_chunk(0);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- layer-0 input: this thread's row, k in [0,64) (part 0) or [64,144) (part 1) ---------------------------
+        const float* src = mask_in + (size_t)tile * kMaskK0 * 128 + q * 32 + lane;
+        const int k_begin = part ? 64 : 0, n_grp = part ? 5 : 4;
+#pragma unroll 1
+        for (int grp = 0; grp < n_grp; grp++) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int k = k_begin + grp * 16 + i;
+                v[i] = k < kMaskK0 ? __ldg(src + (size_t)k * 128) : 0.f;
+            }
+            uint32_t hi[8], lo[8];
+            pack_split16(v, hi, lo);
+            tc::tmem_st8(a_rw + (k_begin >> 1) + grp * 8, hi);
+            tc::tmem_st8(a_rw + kColsAlo + (k_begin >> 1) + grp * 8, lo);
+        }
+        tc::tmem_st_wait();
+        // ---- layer 0: 143(+1) -> 256 ------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int c = 0; c < kNCh0; c++)
+            consume([&](uint32_t saddr) { issue_chunk<kMaskH, kCh0>(d_mma, a_mma + c * (kCh0 / 2), saddr, c > 0 ? 1u : 0u); }, c == kNCh0 - 1);
+        wait_layer();
+        epilogue_to_a();
+        // ---- layer 1: 256 -> 256 --------------------------------------------------------------------------------------
+#pragma unroll 1
+        for (int c = 0; c < kNCh1; c++)
+            consume([&](uint32_t saddr) { issue_chunk<kMaskH, kCh1>(d_mma, a_mma + c * (kCh1 / 2), saddr, c > 0 ? 1u : 0u); }, c == kNCh1 - 1);
+        wait_layer();
+        epilogue_to_a();
+        // ---- layer 2: 256 -> n_inst (16 output columns), resident image ----------------------------------------------
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            issue_chunk<kMaskNOut, kMaskH>(d_mma, a_mma, w2_saddr, 0u);
+            tc::mma_commit(&bar_done);
+        }
+        __syncwarp();
+        wait_layer();
+        // ---- composite: logits[ray] = sum_samples w * point_masks (renderer.py:384); one warp = one ray ---------------
+        if (part == 0) {
+            uint32_t t[16];
+            tc::tmem_ld16(d_rw, t);
+            tc::tmem_ld_wait();
+            const uint32_t ray = tile * 4 + q;
+            const float w = ray < n_rays ? __ldg(weights + (size_t)ray * 32 + lane) : 0.f;
+#pragma unroll
+            for (int c = 0; c < kMaskNOut; c++) {
+                if (c < (int)n_inst) {   // uniform
+                    float s = __fmul_rn(w, __uint_as_float(t[c]));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                    if (lane == 0 && ray < n_rays) logits[(size_t)ray * n_inst + c] = s;
+                }
+            }
+        }
+        // the next tile's first barrier (inside consume) orders these TMEM reads before the next MMAs overwrite D
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tm, 512);
+}
+
+}  // namespace sanerf
+
+using namespace sanerf;
+
+extern "C" {
+
+size_t sanerf_mask_mlp_workspace_bytes(void) { return (size_t)kImgTotal * sizeof(__nv_bfloat16); }
+
+int sanerf_mask_mlp(const float* mask_in_tiled, const float* weights, const float* w0, const float* w1, const float* w2, uint32_t n_inst,
+                    uint32_t n_rays, void* workspace, float* logits, sanerf_stream_t stream) {
+    if (n_rays == 0) return 0;
+    if (!mask_in_tiled || !weights || !w0 || !w1 || !w2 || !workspace || !logits) return SANERF_E_NULL;
+    if (n_inst == 0 || n_inst > (uint32_t)kMaskNOut) return SANERF_E_CONFIG;
+    cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(workspace);
+    mask_prepare_kernel<<<64, 256, 0, st>>>(w0, w1, w2, n_inst, img);
+    const size_t smem = 2 * (size_t)kStageBytes + (size_t)kImg2 * 2;
+    if (cudaFuncSetAttribute(mask_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return SANERF_E_SMEM;
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t n_tiles = div_up(n_rays, 4u);
+    mask_mlp_kernel<<<n_tiles < (uint32_t)sms ? n_tiles : (uint32_t)sms, kHeadThreads, smem, st>>>(mask_in_tiled, weights, img, logits, n_tiles,
+                                                                                                  n_rays, n_inst);
+    return check_launch();
+}
+
+}  // extern "C"

@@ -71,6 +71,7 @@ struct RenderParams {
     float* wsum;
     float* sam_in;
     float* mask_in;
+    uint32_t mask_tiled;
     int16_t* inds0;
     int16_t* inds1;
     float* weights2;
@@ -713,7 +714,11 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         // ---- object head input: per-sample cat[m_grid(x), geo_feat] (renderer.py:304-305, 378) ---
         if constexpr (MASK) if (active) {
             const int nl = (int)p.mgrid.L;
-            float* dst = p.mask_in + ((size_t)ray * 32 + home) * (8 * nl + 15);
+            // row-major [ray,32,K] (reference tensor layout) or tile-transposed [row/128][K][128] for the tensor-core head
+            // (heads.cu): there lane <-> consecutive row, so every store below is one coalesced 128-byte line per warp
+            const size_t row = (size_t)ray * 32 + home;
+            const size_t kstride = p.mask_tiled ? 128 : 1;
+            float* dst = p.mask_tiled ? p.mask_in + (row >> 7) * (size_t)(8 * nl + 15) * 128 + (row & 127) : p.mask_in + row * (8 * nl + 15);
 #pragma unroll 1
             for (int l = 0; l < nl; l++) {
                 float o[8];
@@ -724,10 +729,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                     for (int c = 0; c < 8; c++) o[c] = 0.f;
                 }
 #pragma unroll
-                for (int c = 0; c < 8; c++) dst[8 * l + c] = o[c];
+                for (int c = 0; c < 8; c++) dst[(8 * l + c) * kstride] = o[c];
             }
 #pragma unroll
-            for (int c = 0; c < 15; c++) dst[8 * nl + c] = f16[c + 1];
+            for (int c = 0; c < 15; c++) dst[(8 * nl + c) * kstride] = f16[c + 1];
         }
         __syncwarp();
     }
@@ -852,7 +857,7 @@ int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf
     p.cnf = a->cam_near_far; p.cnf_rows = a->cam_near_far_rows;
     p.bg = a->bg_color; p.bg_rows = a->bg_rows; p.bg_scalar = a->bg_scalar;
     p.image = a->image; p.depth = a->depth; p.wsum = a->weights_sum;
-    p.sam_in = a->sam_in; p.mask_in = a->mask_in;
+    p.sam_in = a->sam_in; p.mask_in = a->mask_in; p.mask_tiled = a->mask_in_tiled;
     p.inds0 = a->inds0; p.inds1 = a->inds1; p.weights2 = a->weights2; p.sigma2 = a->sigma2; p.bins2 = a->bins2; p.f_image = a->f_image;
 
     const uint32_t PL = m->prop_grid[0].num_levels, GL = m->grid.num_levels;

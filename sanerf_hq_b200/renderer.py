@@ -322,13 +322,24 @@ class NeRFRenderer(nn.Module):
                 results["samvit"] = self._samvit_head(sam_in).view(H, W, -1)
             return results
 
-        # object head: per-sample mask_mlp inputs are materialised chunk-wise to bound memory
+        # object head.  The per-sample mask_mlp inputs cat[m_grid(x), geo_feat] are written by the fused kernel for a chunk of
+        # rays at a time (bounds the scratch to `chunk`*32*143 floats) and consumed by the tensor-core head (csrc/heads.cu:
+        # mask_mlp 143 -> 256 -> 256 -> n_inst + the weighted sum over samples, ONE launch per chunk).  Other widths than the
+        # reference's default (config #1's small network, n_inst > 16) use the same inputs with the nn.Module MLP.
         n_inst = self.opt.n_inst
         logits = torch.empty(N, n_inst, device=device)
         width = self.mask_mlp[0].dim_in
-        chunk = max(1, min(N, int(getattr(self.opt, "max_ray_batch", 4096)) * 8))
-        mask_in = torch.empty(chunk, 32, width, device=device)
+        net = self.mask_mlp[0].net
+        tc_head = (width == 143 and len(net) == 3 and net[0].weight.shape == (256, 143) and net[1].weight.shape == (256, 256)
+                   and net[2].weight.shape == (n_inst, 256) and n_inst <= 16 and all(l.bias is None for l in net))
+        chunk = max(4, min(-(-N // 4) * 4, 131072 if tc_head else int(getattr(self.opt, "max_ray_batch", 4096)) * 8))
+        mask_in = torch.empty(chunk * 32 * width, device=device)
         w2 = torch.empty(chunk, 32, device=device)
+        if tc_head:
+            if getattr(self, "_mask_ws", None) is None or self._mask_ws.device != device:
+                self._mask_ws = torch.empty(lib.sanerf_mask_mlp_workspace_bytes(), dtype=torch.uint8, device=device)
+            mw = [l.weight.detach().contiguous() for l in net]
+            a.mask_in_tiled = 1
         sam_full = torch.empty(N, self.samvit_mlp[0].dim_in, device=device) if want_sam else None
         base = {f: getattr(a, f) for f in ("rays_o", "rays_d", "image", "depth", "weights_sum", "cam_near_far", "bg_color",
                                            "inds0", "inds1", "weights2", "sigma2", "bins2", "f_image")}
@@ -350,12 +361,18 @@ class NeRFRenderer(nn.Module):
                 a.weights2 = w2.data_ptr()
             if want_sam:
                 a.sam_in = sam_full.data_ptr() + head * sam_full.shape[1] * 4
+            wts = taps["weights2"][head:head + n] if user_w2 else w2[:n]
             with torch.cuda.device(device):
                 _lib.check(lib.sanerf_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "sanerf_render")
                 _lib.count_launch()
-            wts = taps["weights2"][head:head + n] if user_w2 else w2[:n]
-            point_masks = self.mask_mlp(mask_in[:n])
-            logits[head:head + n] = torch.sum(wts.unsqueeze(-1) * point_masks, dim=-2)
+                if tc_head:
+                    out = logits[head:head + n]
+                    _lib.check(lib.sanerf_mask_mlp(_lib.ptr(mask_in), _lib.ptr(wts), _lib.ptr(mw[0]), _lib.ptr(mw[1]), _lib.ptr(mw[2]),
+                                                   n_inst, n, _lib.ptr(self._mask_ws), _lib.ptr(out), _lib.stream_ptr()), "sanerf_mask_mlp")
+                    _lib.count_launch(2)
+            if not tc_head:
+                point_masks = self.mask_mlp(mask_in[:n * 32 * width].view(n, 32, width))
+                logits[head:head + n] = torch.sum(wts.unsqueeze(-1) * point_masks, dim=-2)
         if want_sam:
             results["samvit"] = self._samvit_head(sam_full).view(H, W, -1)
         results["instance_mask_logits"] = logits

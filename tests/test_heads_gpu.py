@@ -1,0 +1,61 @@
+"""GPU: the tensor-core object head (`sanerf_mask_mlp`, csrc/heads.cu) through the C ABI vs a float64 evaluation of the
+reference's `mask_mlp` + compositing (nerf/renderer.py:376-385, nerf/network.py:31-66: bias-free SkipConnMLP
+143 -> 256 -> 256 -> n_inst, leaky_relu(0.01) between layers; logits = sum_samples w * point_masks)."""
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _tile_transpose(x):
+    """[n_rays, 32, K] -> the [ceil(n_rays*32/128)][K][128] layout sanerf_render writes with mask_in_tiled=1."""
+    n, s, k = x.shape
+    rows = x.reshape(n * s, k)
+    pad = (-rows.shape[0]) % 128
+    if pad:
+        rows = torch.cat([rows, torch.full((pad, k), float("nan"))])      # unused rows: garbage must not leak into real rows
+    return rows.view(-1, 128, k).permute(0, 2, 1).contiguous()
+
+
+@pytest.mark.parametrize("n_rays,n_inst", [(1, 2), (3, 2), (4, 2), (5, 3), (640, 2), (4099, 16), (50000, 2)])
+def test_mask_head_matches_fp64(n_rays, n_inst):
+    from sanerf_hq_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(n_rays * 31 + n_inst)
+    x = torch.rand(n_rays, 32, 143, generator=g) * 2 - 1
+    x[..., 128:] *= 3.0                                           # geo_feat channels: MLP outputs, larger range
+    w = torch.rand(n_rays, 32, generator=g) ** 4
+    w = w / w.sum(-1, keepdim=True).clamp(min=1e-6)
+    bound = lambda fan_in: 1 / fan_in ** 0.5
+    ws = [(torch.rand(256, 143, generator=g) * 2 - 1) * bound(143), (torch.rand(256, 256, generator=g) * 2 - 1) * bound(256),
+          (torch.rand(n_inst, 256, generator=g) * 2 - 1) * bound(256)]
+    h = x.double()
+    for i, m in enumerate(ws):
+        h = h @ m.double().t()
+        if i < 2:
+            h = torch.nn.functional.leaky_relu(h, 0.01)
+    want = (w.double().unsqueeze(-1) * h).sum(-2)
+
+    xin = _tile_transpose(x).to(DEV)
+    wd = [m.to(DEV).contiguous() for m in ws]
+    wts = w.to(DEV)
+    work = torch.empty(lib.sanerf_mask_mlp_workspace_bytes(), dtype=torch.uint8, device=DEV)
+    out = torch.full((n_rays, n_inst), float("nan"), device=DEV)
+    _lib.check(lib.sanerf_mask_mlp(_lib.ptr(xin), _lib.ptr(wts), _lib.ptr(wd[0]), _lib.ptr(wd[1]), _lib.ptr(wd[2]), n_inst, n_rays,
+                                   _lib.ptr(work), _lib.ptr(out), _lib.stream_ptr()), "mask_mlp")
+    torch.cuda.synchronize()
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    # bf16 hi/lo split operands: 2^-17 per operand, random accumulation over <= 256 terms and three layers
+    scale = float(want.abs().max())
+    assert ((got - want).abs().max() / scale).item() < 1e-4
+    assert rel_err(got, want, floor=0.1 * float(want.pow(2).mean().sqrt())) < 1e-3      # the render-path tolerance for logits
+    # same result when the rays are processed with a different tiling (pointer shifted by one tile = 4 rays)
+    if n_rays > 8:
+        out2 = torch.empty(n_rays - 4, n_inst, device=DEV)
+        _lib.check(lib.sanerf_mask_mlp(xin[1:].contiguous().data_ptr(), wts[4:].contiguous().data_ptr(), _lib.ptr(wd[0]), _lib.ptr(wd[1]),
+                                       _lib.ptr(wd[2]), n_inst, n_rays - 4, _lib.ptr(work), _lib.ptr(out2), _lib.stream_ptr()), "mask_mlp")
+        assert torch.equal(out2, out[4:])
