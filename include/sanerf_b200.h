@@ -209,6 +209,14 @@ size_t sanerf_mask_mlp_workspace_bytes(void);
 int sanerf_mask_mlp(const float *mask_in_tiled, const float *weights, const float *w0, const float *w1, const float *w2,
                     uint32_t n_inst, uint32_t n_rays, void *workspace, float *logits, sanerf_stream_t stream);
 
+/* SAM feature head on the tensor cores: samvit = LayerNorm(SkipConnMLP(f)) per ray (nerf/renderer.py:361-369,
+ * nerf/network.py:113-116): sam_in [n_rays (buffer padded to a multiple of 128 rows), 163] row-major as written by
+ * sanerf_render; w[5] / b[5]: samvit_mlp.0.net.{0..4}.{weight,bias} ([256,163] [256,256] [256,419] [256,256] [256,256]);
+ * ln_w / ln_b: samvit_mlp.1 (LayerNorm 256, eps 1e-5); out [n_rays,256].  w and b are HOST arrays of device pointers. */
+size_t sanerf_samvit_mlp_workspace_bytes(void);
+int sanerf_samvit_mlp(const float *sam_in, const float *const *w, const float *const *b, const float *ln_w, const float *ln_b,
+                      uint32_t n_rays, void *workspace, float *out, sanerf_stream_t stream);
+
 /* Validation entry point for the tcgen05 (5th-gen tensor core) MLP path that the fused render uses for grid_mlp
  * (nerf/network.py:9-29 `MLP`, bias-free, ReLU between layers): out[M,16] = relu(relu(x W0^T) W1^T) W2^T with
  * x [M,K], W0 [H,K], W1 [H,H], W2 [16,H] in nn.Linear layout, fp32 in/out, split-precision (3xTF32) tensor-core math.

@@ -55,6 +55,8 @@ PROTOTYPES = {
     "sanerf_mlp3_tc": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp],
     "sanerf_mask_mlp_workspace_bytes": [],
     "sanerf_mask_mlp": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp],
+    "sanerf_samvit_mlp_workspace_bytes": [],
+    "sanerf_samvit_mlp": [_vp, _vp * 5, _vp * 5, _vp, _vp, _u32, _vp, _vp, _vp],
     "sanerf_abi_version": [],
     "sanerf_error_string": [_i32],
 }
@@ -88,7 +90,7 @@ def load():
         fn = getattr(L, name)
         fn.argtypes = argtypes
         fn.restype = (ctypes.c_char_p if name == "sanerf_error_string" else
-                      ctypes.c_size_t if name == "sanerf_mask_mlp_workspace_bytes" else ctypes.c_int)
+                      ctypes.c_size_t if name.endswith("_workspace_bytes") else ctypes.c_int)
     _lib = L
     return L
 

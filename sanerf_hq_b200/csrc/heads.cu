@@ -268,6 +268,270 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
     if (warp == 0) tc::tmem_dealloc(tm, 512);
 }
 
+
+// =====================================================================================================================
+// SAM feature head: samvit = LayerNorm(SkipConnMLP(f)),  f = cat[f_sam(128), f_image(31), image(3), depth(1)]  (163)
+// Reference: nerf/renderer.py:361-369, nerf/network.py:113-116, 31-66: five Linear layers WITH bias, width 256,
+// leaky_relu(0.01) after all but the last, the 163-d input re-concatenated (hidden first) in front of layer 2
+// (weight [256, 256+163]), then nn.LayerNorm(256, eps=1e-5).  Runs once per RAY (0.69 MFLOP each).
+// Same machinery as the object head: 128 rays per tile, activations in TMEM (bf16 hi | lo), weight K-chunks streamed through
+// the cp.async ring.  Layer 2 is two accumulating phases: A = hidden (K=256), then A = the input tile again (K=163 -> 176).
+// The input tile (row-major [128,163] fp32, 83 KB) is staged once in shared memory and used by both phases.
+// =====================================================================================================================
+constexpr int kSamIn = 163, kSamInP = 176, kSamW = 256;
+struct SamChunk {
+    uint32_t img_off;   // bf16 elements from the start of the image workspace
+    uint16_t kc;        // K of the chunk (48 or 64)
+    uint16_t a_col;     // first A column (hi part)
+    uint8_t first;      // 1: first chunk of an accumulation (D is overwritten)
+    uint8_t last;       // 1: last chunk before the activations are read back
+    uint8_t layer;      // source weight matrix 0..4
+    uint8_t pad;
+    uint16_t k0;        // first source column of the chunk in that matrix
+    uint16_t kvalid;    // number of real (non-padding) columns in the chunk
+};
+constexpr int kSamChunks = 22;
+__constant__ SamChunk c_sam_chunks[kSamChunks];
+
+__global__ void sam_prepare_kernel(const float* __restrict__ w0, const float* __restrict__ w1, const float* __restrict__ w2,
+                                   const float* __restrict__ w3, const float* __restrict__ w4, __nv_bfloat16* __restrict__ img) {
+    const float* ws[5] = {w0, w1, w2, w3, w4};
+    const int fan_in[5] = {kSamIn, kSamW, kSamW + kSamIn, kSamW, kSamW};
+    for (int c = blockIdx.y; c < kSamChunks; c += gridDim.y) {
+        const SamChunk ch = c_sam_chunks[c];
+        const float* w = ws[ch.layer];
+        const int fi = fan_in[ch.layer];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kSamW * ch.kc; i += gridDim.x * blockDim.x) {
+            const int n = i / ch.kc, kk = i % ch.kc;
+            __nv_bfloat16 h, l;
+            split_bf16(kk < ch.kvalid ? w[(size_t)n * fi + ch.k0 + kk] : 0.f, h, l);
+            img[ch.img_off + img_index(n, kk, kSamW)] = h;
+            img[ch.img_off + kSamW * ch.kc + img_index(n, kk, kSamW)] = l;
+        }
+    }
+}
+
+template <int KC>
+__device__ __forceinline__ void issue_chunk_rt(uint32_t d_tmem, uint32_t a_col, uint32_t img_saddr, uint32_t first_accumulate) {
+    issue_chunk<kSamW, KC>(d_tmem, a_col, img_saddr, first_accumulate);
+}
+
+__global__ void __launch_bounds__(kHeadThreads, 1)
+    samvit_mlp_kernel(const float* __restrict__ sam_in, const __nv_bfloat16* __restrict__ img, const float* __restrict__ b0,
+                      const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ b3, const float* __restrict__ b4,
+                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ out, uint32_t n_tiles, uint32_t n_rays) {
+    extern __shared__ __align__(128) uint8_t smem[];   // [2 stages x 64 KB][input tile 128 x 163 fp32]
+    __shared__ __align__(8) uint64_t bar_free[2], bar_done;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, part = warp >> 2;
+    const uint32_t stage_saddr = tc::smem_u32(smem);
+    float* xt = reinterpret_cast<float*>(smem + 2 * kStageBytes);
+    const uint32_t xt_saddr = stage_saddr + 2 * kStageBytes;
+    if (tid == 0) {
+        tc::mbar_init(&bar_free[0], 1);
+        tc::mbar_init(&bar_free[1], 1);
+        tc::mbar_init(&bar_done, 1);
+        tc::fence_mbar_init();
+    }
+    if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tm = tmem_base_s, a_mma = tm, d_mma = tm + kColsD;
+    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+    const uint32_t a_rw = a_mma + lane_base, d_rw = d_mma + lane_base;
+    uint32_t ph_free[2] = {0, 0}, ph_done = 0;
+    const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t total_chunks = my_tiles * kSamChunks;
+    const int row = q * 32 + lane;
+
+    auto load_chunk = [&](uint32_t g) {
+        const SamChunk ch = c_sam_chunks[g % kSamChunks];
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(img + ch.img_off);
+        const uint32_t bytes = 2u * kSamW * ch.kc * 2u, dst = stage_saddr + (g & 1) * kStageBytes;
+        for (uint32_t i = tid; i < bytes / 16; i += kHeadThreads) cp_async16(dst + i * 16, src + i * 16);
+        cp_async_commit();
+    };
+    uint32_t g = 0;
+    // consume the next chunk of the stream (see mask_mlp_kernel::consume)
+    auto consume = [&] {
+        const SamChunk ch = c_sam_chunks[g % kSamChunks];
+        cp_async_wait_all();
+        tc::fence_proxy_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t saddr = stage_saddr + (g & 1) * kStageBytes;
+            if (ch.kc == 64) issue_chunk_rt<64>(d_mma, a_mma + ch.a_col, saddr, ch.first ? 0u : 1u);
+            else issue_chunk_rt<48>(d_mma, a_mma + ch.a_col, saddr, ch.first ? 0u : 1u);
+            tc::mma_commit(&bar_free[g & 1]);
+            if (ch.last) tc::mma_commit(&bar_done);
+        }
+        __syncwarp();
+        if (g + 1 < total_chunks) {
+            if (g >= 1) {
+                tc::mbar_wait(&bar_free[(g + 1) & 1], ph_free[(g + 1) & 1]);
+                ph_free[(g + 1) & 1] ^= 1;
+            }
+            load_chunk(g + 1);
+        }
+        g++;
+    };
+    auto wait_layer = [&] {
+        tc::mbar_wait(&bar_done, ph_done);
+        ph_done ^= 1;
+        tc::fence_after_sync();
+    };
+    // the 163-d input row of this thread (from the shared-memory tile) -> A columns; part 0: k [0,96), part 1: k [96,176)
+    auto stage_input = [&] {
+        const float* xr = xt + row * kSamIn;
+        const int k_begin = part ? 96 : 0, n_grp = part ? 5 : 6;
+#pragma unroll 1
+        for (int grp = 0; grp < n_grp; grp++) {
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const int k = k_begin + grp * 16 + i;
+                v[i] = k < kSamIn ? xr[k] : 0.f;
+            }
+            uint32_t hi[8], lo[8];
+            pack_split16(v, hi, lo);
+            tc::tmem_st8(a_rw + (k_begin >> 1) + grp * 8, hi);
+            tc::tmem_st8(a_rw + kColsAlo + (k_begin >> 1) + grp * 8, lo);
+        }
+        tc::tmem_st_wait();
+    };
+    // D[:, part*128 .. +128) + bias -> leaky_relu -> bf16 hi/lo -> A columns of the next layer
+    auto epilogue_to_a = [&](const float* __restrict__ bias) {
+#pragma unroll 1
+        for (int grp = 0; grp < 8; grp++) {
+            uint32_t t[16];
+            tc::tmem_ld16(d_rw + part * 128 + grp * 16, t);
+            tc::tmem_ld_wait();
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                const float x = __uint_as_float(t[i]) + __ldg(bias + part * 128 + grp * 16 + i);
+                v[i] = x > 0.f ? x : 0.01f * x;
+            }
+            uint32_t hi[8], lo[8];
+            pack_split16(v, hi, lo);
+            tc::tmem_st8(a_rw + part * 64 + grp * 8, hi);
+            tc::tmem_st8(a_rw + kColsAlo + part * 64 + grp * 8, lo);
+        }
+        tc::tmem_st_wait();
+    };
+
+    if (total_chunks) load_chunk(0);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        // ---- input tile [128,163] fp32 -> shared memory (coalesced 16-byte copies; the buffer is padded to whole tiles) ----
+        __syncthreads();   // the previous tile's readers of xt are done
+        {
+            const float4* src = reinterpret_cast<const float4*>(sam_in + (size_t)tile * 128 * kSamIn);
+            float4* dst = reinterpret_cast<float4*>(xt);
+            for (int i = tid; i < 128 * kSamIn / 4; i += kHeadThreads) dst[i] = __ldg(src + i);
+        }
+        __syncthreads();
+        (void)xt_saddr;
+        stage_input();
+        for (int c = 0; c < 3; c++) consume();          // layer 0: 163 -> 256
+        wait_layer();
+        epilogue_to_a(b0);
+        for (int c = 0; c < 4; c++) consume();          // layer 1
+        wait_layer();
+        epilogue_to_a(b1);
+        for (int c = 0; c < 4; c++) consume();          // layer 2, hidden part  (columns 0..255 of the [256,419] weight)
+        wait_layer();                                   // the MMAs have read A: it can be overwritten with the input again
+        stage_input();
+        for (int c = 0; c < 3; c++) consume();          // layer 2, skip part    (columns 256..418), accumulates onto D
+        wait_layer();
+        epilogue_to_a(b2);
+        for (int c = 0; c < 4; c++) consume();          // layer 3
+        wait_layer();
+        epilogue_to_a(b3);
+        for (int c = 0; c < 4; c++) consume();          // layer 4 (no activation)
+        wait_layer();
+        // ---- bias + LayerNorm(256, eps 1e-5, affine) + store; one thread per ray (part 0), three passes over its TMEM row ----
+        if (part == 0) {
+            const uint32_t ray = tile * 128 + row;
+            float mean = 0.f;
+#pragma unroll 1
+            for (int grp = 0; grp < 16; grp++) {
+                uint32_t t[16];
+                tc::tmem_ld16(d_rw + grp * 16, t);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i++) mean += __uint_as_float(t[i]) + __ldg(b4 + grp * 16 + i);
+            }
+            mean *= (1.0f / kSamW);
+            float var = 0.f;
+#pragma unroll 1
+            for (int grp = 0; grp < 16; grp++) {
+                uint32_t t[16];
+                tc::tmem_ld16(d_rw + grp * 16, t);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float dlt = __uint_as_float(t[i]) + __ldg(b4 + grp * 16 + i) - mean;
+                    var = __fmaf_rn(dlt, dlt, var);
+                }
+            }
+            const float rstd = rsqrtf(var * (1.0f / kSamW) + 1e-5f);
+#pragma unroll 1
+            for (int grp = 0; grp < 16; grp++) {
+                uint32_t t[16];
+                tc::tmem_ld16(d_rw + grp * 16, t);
+                tc::tmem_ld_wait();
+                if (ray < n_rays) {
+                    float* dst = out + (size_t)ray * kSamW + grp * 16;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4) {
+                        float y[4];
+#pragma unroll
+                        for (int j = 0; j < 4; j++) {
+                            const int c = grp * 16 + i + j;
+                            y[j] = (__uint_as_float(t[i + j]) + __ldg(b4 + c) - mean) * rstd * __ldg(ln_w + c) + __ldg(ln_b + c);
+                        }
+                        *reinterpret_cast<float4*>(dst + i) = make_float4(y[0], y[1], y[2], y[3]);
+                    }
+                }
+            }
+        }
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tm, 512);
+}
+
+static size_t sam_build_chunks(SamChunk* out) {
+    // (layer, k0 in the source matrix, number of valid columns) per accumulation phase; each is cut into 64/48-wide chunks
+    struct Phase { int layer, k0, kvalid; };
+    const Phase phases[6] = {{0, 0, kSamIn}, {1, 0, kSamW}, {2, 0, kSamW}, {2, kSamW, kSamIn}, {3, 0, kSamW}, {4, 0, kSamW}};
+    size_t off = 0;
+    int n = 0;
+    for (const Phase& ph : phases) {
+        const int kp = (ph.kvalid + 15) / 16 * 16;
+        for (int k = 0; k < kp;) {
+            const int kc = (kp - k) >= 64 ? 64 : (kp - k);   // 176 = 64 + 64 + 48
+            SamChunk& c = out[n++];
+            c.img_off = (uint32_t)off;
+            c.kc = (uint16_t)kc;
+            c.a_col = (uint16_t)(k / 2);
+            // layer 2's second phase accumulates onto the first
+            c.first = (k == 0 && !(ph.layer == 2 && ph.k0 != 0)) ? 1 : 0;
+            c.last = (k + kc >= kp) ? 1 : 0;
+            c.layer = (uint8_t)ph.layer;
+            c.pad = 0;
+            c.k0 = (uint16_t)(ph.k0 + k);
+            c.kvalid = (uint16_t)((ph.kvalid - k) < kc ? (ph.kvalid - k > 0 ? ph.kvalid - k : 0) : kc);
+            off += 2 * (size_t)kSamW * kc;
+            k += kc;
+        }
+    }
+    return n == kSamChunks ? off : 0;
+}
+
 }  // namespace sanerf
 
 using namespace sanerf;
@@ -295,6 +559,38 @@ int sanerf_mask_mlp(const float* mask_in_tiled, const float* weights, const floa
     const uint32_t n_tiles = div_up(n_rays, 4u);
     mask_mlp_kernel<<<n_tiles < (uint32_t)sms ? n_tiles : (uint32_t)sms, kHeadThreads, smem, st>>>(mask_in_tiled, weights, img, logits, n_tiles,
                                                                                                   n_rays, n_inst);
+    return check_launch();
+}
+
+size_t sanerf_samvit_mlp_workspace_bytes(void) {
+    SamChunk tmp[kSamChunks + 8];
+    return sam_build_chunks(tmp) * sizeof(__nv_bfloat16);
+}
+
+int sanerf_samvit_mlp(const float* sam_in, const float* const* w, const float* const* b, const float* ln_w, const float* ln_b, uint32_t n_rays,
+                      void* workspace, float* out, sanerf_stream_t stream) {
+    if (n_rays == 0) return 0;
+    if (!sam_in || !w || !b || !ln_w || !ln_b || !workspace || !out) return SANERF_E_NULL;
+    for (int i = 0; i < 5; i++)
+        if (!w[i] || !b[i]) return SANERF_E_NULL;
+    cudaStream_t st = (cudaStream_t)stream;
+    SamChunk chunks[kSamChunks + 8];
+    if (sam_build_chunks(chunks) == 0) return SANERF_E_CONFIG;
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_sam_chunks, chunks, sizeof(SamChunk) * kSamChunks, 0, cudaMemcpyHostToDevice, st);
+    if (e != cudaSuccess) return (int)e;
+    __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(workspace);
+    sam_prepare_kernel<<<dim3(16, kSamChunks), 256, 0, st>>>(w[0], w[1], w[2], w[3], w[4], img);
+    const size_t smem = 2 * (size_t)kStageBytes + (size_t)128 * kSamIn * sizeof(float);
+    if (cudaFuncSetAttribute(samvit_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return SANERF_E_SMEM;
+    }
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t n_tiles = div_up(n_rays, 128u);
+    samvit_mlp_kernel<<<n_tiles < (uint32_t)sms ? n_tiles : (uint32_t)sms, kHeadThreads, smem, st>>>(
+        sam_in, img, b[0], b[1], b[2], b[3], b[4], ln_w, ln_b, out, n_tiles, n_rays);
     return check_launch();
 }
 

@@ -313,7 +313,7 @@ class NeRFRenderer(nn.Module):
         if not want_mask:
             sam_in = None
             if want_sam:
-                sam_in = torch.empty(N, self.samvit_mlp[0].dim_in, device=device)
+                sam_in = self._alloc_rows_padded(N, self.samvit_mlp[0].dim_in, device)
                 a.sam_in = sam_in.data_ptr()
             with torch.cuda.device(device):
                 _lib.check(lib.sanerf_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "sanerf_render")
@@ -340,7 +340,7 @@ class NeRFRenderer(nn.Module):
                 self._mask_ws = torch.empty(lib.sanerf_mask_mlp_workspace_bytes(), dtype=torch.uint8, device=device)
             mw = [l.weight.detach().contiguous() for l in net]
             a.mask_in_tiled = 1
-        sam_full = torch.empty(N, self.samvit_mlp[0].dim_in, device=device) if want_sam else None
+        sam_full = self._alloc_rows_padded(N, self.samvit_mlp[0].dim_in, device) if want_sam else None
         base = {f: getattr(a, f) for f in ("rays_o", "rays_d", "image", "depth", "weights_sum", "cam_near_far", "bg_color",
                                            "inds0", "inds1", "weights2", "sigma2", "bins2", "f_image")}
         strides = {"rays_o": 12, "rays_d": 12, "image": 12, "depth": 4, "weights_sum": 4, "inds0": 130, "inds1": 66,
@@ -378,8 +378,37 @@ class NeRFRenderer(nn.Module):
         results["instance_mask_logits"] = logits
         return results
 
+    @staticmethod
+    def _alloc_rows_padded(n, width, device, multiple=128):
+        """[n, width] view of a buffer with whole tiles of `multiple` rows (the tensor-core heads read full tiles)."""
+        return torch.empty(-(-max(n, 1) // multiple) * multiple, width, device=device)[:n]
+
     def _samvit_head(self, f):
-        return self.samvit_mlp(f)
+        """samvit_mlp (SkipConnMLP + LayerNorm, network.py:113-116) of the composited per-ray features f [n,163].
+        No-grad CUDA input with the reference's shapes -> the tensor-core head (csrc/heads.cu); anything else -> nn.Modules."""
+        mlp, ln = self.samvit_mlp[0], self.samvit_mlp[1]
+        net = mlp.net
+        ok = (f.is_cuda and not torch.is_grad_enabled() and f.dim() == 2 and f.shape[1] == 163 and len(net) == 5
+              and list(mlp.skip_layers) == [2] and [tuple(l.weight.shape) for l in net] ==
+              [(256, 163), (256, 256), (256, 419), (256, 256), (256, 256)] and all(l.bias is not None for l in net)
+              and tuple(ln.normalized_shape) == (256,) and abs(ln.eps - 1e-5) < 1e-12 and ln.weight is not None
+              and f.untyped_storage().nbytes() - f.storage_offset() * 4 >= -(-f.shape[0] // 128) * 128 * 163 * 4)
+        if not ok:
+            return self.samvit_mlp(f)
+        lib = _lib.load()
+        n, device = f.shape[0], f.device
+        if getattr(self, "_sam_ws", None) is None or self._sam_ws.device != device:
+            self._sam_ws = torch.empty(lib.sanerf_samvit_mlp_workspace_bytes(), dtype=torch.uint8, device=device)
+        ws = [l.weight.detach().contiguous() for l in net]
+        bs = [l.bias.detach().contiguous() for l in net]
+        out = torch.empty(n, 256, device=device)
+        wp = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in ws])
+        bp = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in bs])
+        with torch.cuda.device(device):
+            _lib.check(lib.sanerf_samvit_mlp(_lib.ptr(f), wp, bp, _lib.ptr(ln.weight.detach()), _lib.ptr(ln.bias.detach()), n,
+                                             _lib.ptr(self._sam_ws), _lib.ptr(out), _lib.stream_ptr()), "sanerf_samvit_mlp")
+            _lib.count_launch(2)
+        return out
 
     # ------------------------------------------------------------------------------------------
     # composed path (differentiable; also the perturb=True path)

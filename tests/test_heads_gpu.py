@@ -59,3 +59,42 @@ def test_mask_head_matches_fp64(n_rays, n_inst):
         _lib.check(lib.sanerf_mask_mlp(xin[1:].contiguous().data_ptr(), wts[4:].contiguous().data_ptr(), _lib.ptr(wd[0]), _lib.ptr(wd[1]),
                                        _lib.ptr(wd[2]), n_inst, n_rays - 4, _lib.ptr(work), _lib.ptr(out2), _lib.stream_ptr()), "mask_mlp")
         assert torch.equal(out2, out[4:])
+
+
+@pytest.mark.parametrize("n_rays", [1, 127, 128, 129, 4000, 70001])
+def test_samvit_head_matches_fp64(n_rays):
+    """sanerf_samvit_mlp vs float64: five biased layers, skip concat (hidden first) before layer 2, leaky_relu, LayerNorm."""
+    import ctypes
+    from sanerf_hq_b200 import _lib
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(n_rays)
+    x = torch.randn(n_rays, 163, generator=g)
+    dims = [(256, 163), (256, 256), (256, 419), (256, 256), (256, 256)]
+    ws = [(torch.rand(o, i, generator=g) * 2 - 1) / i ** 0.5 for o, i in dims]
+    bs = [(torch.rand(o, generator=g) * 2 - 1) / i ** 0.5 for o, i in dims]
+    ln_w, ln_b = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.1
+    h = x.double()
+    for l in range(5):
+        if l == 2:
+            h = torch.cat([h, x.double()], dim=-1)
+        h = h @ ws[l].double().t() + bs[l].double()
+        if l != 4:
+            h = torch.nn.functional.leaky_relu(h, 0.01)
+    want = torch.nn.functional.layer_norm(h, (256,), ln_w.double(), ln_b.double(), 1e-5)
+
+    pad = -(-n_rays // 128) * 128
+    xin = torch.full((pad, 163), float("nan"), device=DEV)
+    xin[:n_rays] = x.to(DEV)
+    wd, bd = [w.to(DEV).contiguous() for w in ws], [b.to(DEV).contiguous() for b in bs]
+    lw, lb = ln_w.to(DEV), ln_b.to(DEV)
+    work = torch.empty(lib.sanerf_samvit_mlp_workspace_bytes(), dtype=torch.uint8, device=DEV)
+    out = torch.full((n_rays, 256), float("nan"), device=DEV)
+    wp = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in wd])
+    bp = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in bd])
+    _lib.check(lib.sanerf_samvit_mlp(_lib.ptr(xin), wp, bp, _lib.ptr(lw), _lib.ptr(lb), n_rays, _lib.ptr(work), _lib.ptr(out),
+                                     _lib.stream_ptr()), "samvit_mlp")
+    torch.cuda.synchronize()
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() < 2e-4 * float(want.abs().max())
+    assert rel_err(got, want, floor=0.1 * float(want.pow(2).mean().sqrt())) < 1e-3
