@@ -286,6 +286,51 @@ __device__ __forceinline__ void gather_levels_x2(const GridDev& g, const float (
     }
 }
 
+// ---- C=8 feature grids: quarter-row gathers -------------------------------------------------------------------------
+// A C=8 row is 32 bytes.  "lane = sample, two LDG.128 per corner" costs 2 L1 tag cycles per distinct 128-byte line per
+// request (tools/l1_gather.cu), with up to 32 lines per request.  Here 4 lanes share a sample, each fetching 8 bytes (2 of
+// the 8 channels) of every corner row: a request covers 8 samples x 4 quarter rows = 8 lines at 1 cycle per line.
+// One level of grid g at point x: this lane's channel pair (2*part, 2*part+1), blended exactly like encode_level.
+__device__ __forceinline__ void quarter_level(const GridDev& g, int l, const float (&x)[3], int part, float& o0, float& o1) {
+    const uint32_t res = g.res[l];
+    const uint32_t hmask = g.hmask[l];
+    const float2* __restrict__ rows = reinterpret_cast<const float2*>(g.base[l]) + part;   // 4 float2 per row
+    const float resf = g.resf[l], top = g.topf[l];
+    uint32_t b0[3], b1[3];
+    float f[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        float pos = fminf(fmaxf(__fmaf_rn(x[d], resf, -0.5f), 0.0f), top);
+        const float fl = floorf(pos);
+        b0[d] = (uint32_t)fl;
+        b1[d] = min(b0[d] + 1, res - 1);
+        f[d] = pos - fl;
+    }
+    float2 v[8];
+    if (hmask == 0) {
+        const uint32_t y0 = b0[1] * res, y1 = b1[1] * res, z0 = b0[2] * res * res, z1 = b1[2] * res * res;
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __ldg(rows + 4 * (((i & 1) ? b1[0] : b0[0]) + ((i & 2) ? y1 : y0) + ((i & 4) ? z1 : z0)));
+    } else {
+        const uint32_t x0 = b0[0] & hmask, x1 = b1[0] & hmask;
+        const uint32_t y0 = (b0[1] * 2654435761u) & hmask, y1 = (b1[1] * 2654435761u) & hmask;
+        const uint32_t z0 = (b0[2] * 805459861u) & hmask, z1 = (b1[2] * 805459861u) & hmask;
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __ldg(rows + 4 * (((i & 1) ? x1 : x0) ^ ((i & 2) ? y1 : y0) ^ ((i & 4) ? z1 : z0)));
+    }
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float ww = (i & 1) ? f[0] : 1 - f[0];
+        ww *= (i & 2) ? f[1] : 1 - f[1];
+        ww *= (i & 4) ? f[2] : 1 - f[2];
+        a0 = __fmaf_rn(ww, v[i].x, a0);
+        a1 = __fmaf_rn(ww, v[i].y, a1);
+    }
+    o0 = a0;
+    o1 = a1;
+}
+
 // y[n] = sum_k W[n][k] x[k], W in shared memory as [N][KP] (KP = K rounded up to 4, zero padded);
 // every lane reads the same address (broadcast LDS.128), activations stay in registers.
 template <int K, int KP, int N, bool RELU>
@@ -684,23 +729,6 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         if constexpr (SAM) if (active) {
             float* dst = p.sam_in + (size_t)ray * (8 * p.sgrid.L + 35);
             const int nl = (int)p.sgrid.L;
-#pragma unroll 1
-            for (int l = 0; l < nl; l++) {
-                float o[8];
-                if (inside) {
-                    encode_level<8>(p.sgrid, l, x01, o);
-                } else {
-#pragma unroll
-                    for (int c = 0; c < 8; c++) o[c] = 0.f;
-                }
-                float keep = 0.f;
-#pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    const float s = warp_sum(__fmul_rn(w, o[c]));
-                    keep = lane == c ? s : keep;
-                }
-                if (lane < 8) dst[8 * l + lane] = keep;
-            }
             float* tail = dst + 8 * nl;
             if (lane < 31) {
                 float v = fimg[0];
@@ -710,6 +738,37 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             }
             if (lane == 31) tail[34] = depth;
             if (lane < 3) tail[31 + lane] = lane == 0 ? rgb[0] : (lane == 1 ? rgb[1] : rgb[2]);
+            // f_sam = sum_samples w * s_grid(x) (renderer.py:361): lanes (s8, part) = (sample mod 8, channel pair); the 32 samples
+            // take 4 passes of 8; the per-sample points and weights come from their owner lanes
+            const int s8 = lane >> 2, part = lane & 3;
+            float xs[4][3], wsmp[4];
+#pragma unroll
+            for (int ps = 0; ps < 4; ps++) {
+                const int srcl = 8 * ps + s8;
+#pragma unroll
+                for (int d = 0; d < 3; d++) xs[ps][d] = __shfl_sync(kFull, x01[d], srcl);
+                wsmp[ps] = __shfl_sync(kFull, inside ? w : 0.f, srcl);   // outside points contribute zeros (gridencoder.cu:105-130)
+            }
+#pragma unroll 1
+            for (int l = 0; l < nl; l++) {
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int ps = 0; ps < 4; ps++) {
+                    float o0, o1;
+                    quarter_level(p.sgrid, l, xs[ps], part, o0, o1);
+                    a0 = __fmaf_rn(wsmp[ps], o0, a0);
+                    a1 = __fmaf_rn(wsmp[ps], o1, a1);
+                }
+#pragma unroll
+                for (int o = 4; o < 32; o <<= 1) {   // sum over the 8 sample slots (lanes with the same channel pair)
+                    a0 += __shfl_xor_sync(kFull, a0, o);
+                    a1 += __shfl_xor_sync(kFull, a1, o);
+                }
+                if (lane < 4) {   // rows of sam_in are 163 floats: no 8-byte alignment, scalar stores
+                    dst[8 * l + 2 * part] = a0;
+                    dst[8 * l + 2 * part + 1] = a1;
+                }
+            }
         }
         // ---- object head input: per-sample cat[m_grid(x), geo_feat] (renderer.py:304-305, 378) ---
         if constexpr (MASK) if (active) {
