@@ -18,7 +18,7 @@ SO = os.path.join(LIBDIR, "libsanerf_b200.so")
 SOURCES = ["grid_encode.cu", "sh_encode.cu", "freq_encode.cu", "render.cu", "mlp_tc.cu", "heads.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc.cuh"), os.path.join(os.path.dirname(HERE), "include", "sanerf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "--threads", "2"]
+              "-Xcompiler", "-fPIC", "--threads", "2"] + os.environ.get("SANERF_NVCC_FLAGS", "").split()
 
 
 def _nvcc():

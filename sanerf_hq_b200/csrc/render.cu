@@ -29,7 +29,14 @@
 
 namespace sanerf {
 
-constexpr int kWarps = 16;              // warps (= rays in flight) per CTA
+#ifndef SANERF_RENDER_WARPS
+#define SANERF_RENDER_WARPS 16
+#endif
+constexpr int kWarps = SANERF_RENDER_WARPS;   // warps (= rays in flight) per CTA; 4 warps = one tensor-core group
+constexpr int kGroups = kWarps / 4;
+constexpr bool kShareSlots = kGroups > 4;     // more groups than 128-column TMEM slots: time-share them (tc::group_acquire).
+// Measured on B200: 20 warps (96 registers, slot sharing) = 19.1 ms per 800x800 frame vs 13.7 ms for 16 warps (128 registers):
+// the extra spills cost more than the extra warps hide.
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxT = 128;              // samples of the widest stage
 constexpr unsigned kFull = 0xffffffffu;
@@ -518,7 +525,8 @@ __device__ __forceinline__ bool sample_point(const RayCtx& r, float b0, float b1
 
 // proposal stage: T samples through proposal network e; fills ds[] with delta*sigma
 template <int T, int PL, int GL, int HG>
-__device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, const float* sm, tc::Group& grp, const RayCtx& r,
+__device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, const float* sm, tc::Group& grp, unsigned int* free_mask,
+                                               volatile int* my_slot, uint32_t tmem_base, int warp_in_group, const RayCtx& r,
                                                const float* bins, float* ds, int lane) {
     using S = Smem<PL, GL, HG>;
     const GridDev& g = p.prop[e];
@@ -543,7 +551,9 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, con
         }
         // prop_mlp layer 0 (2L -> 16, ReLU; network.py:137,142) on the tensor core: 4 warps x 32 samples = one 128-row MMA tile per chunk
         float ha[16], hb[16];
+        if constexpr (kShareSlots) tc::group_acquire(grp, free_mask, my_slot, tmem_base, warp_in_group);
         tc::group_layer_x2<S::PKP, 16, true>(grp, w0, w0 + 16 * S::PKP, feata, featb, ha, hb);
+        if constexpr (kShareSlots) tc::group_release(grp, free_mask, my_slot);
         float oa = 0.f, ob = 0.f;
 #pragma unroll
         for (int k = 0; k < 16; k += 4) {
@@ -563,20 +573,28 @@ template <int PL, int GL, int HG, int HV, bool SAM, bool MASK>
 __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_constant__ RenderParams p) {
     using S = Smem<PL, GL, HG>;
     extern __shared__ __align__(128) float sm[];
-    __shared__ __align__(8) uint64_t mma_bar[kWarps / 4];
+    __shared__ __align__(8) uint64_t mma_bar[kGroups];
     __shared__ uint32_t tmem_base_s;
+    __shared__ unsigned int tmem_free_mask;
+    __shared__ int tmem_slot_of[kGroups];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     stage_weights<PL, GL, HG, HV>(sm, p);
     if (threadIdx.x == 0) {
-        for (int i = 0; i < kWarps / 4; i++) tc::mbar_init(&mma_bar[i], 1);
+        for (int i = 0; i < kGroups; i++) tc::mbar_init(&mma_bar[i], 1);
         tc::fence_mbar_init();
+        tmem_free_mask = 0xFu;
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);  // one persistent CTA per SM owns all 512 TMEM columns: 4 groups x 128
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     // 4 warps = 4 rays = 128 samples of the final stage form one tensor-core group (one MMA row per thread)
-    tc::Group grp = tc::make_group(tmem_base_s, warp >> 2, warp & 3, lane, &mma_bar[warp >> 2]);
+    tc::Group grp = tc::make_group(tmem_base_s, kShareSlots ? 0 : (warp >> 2), warp & 3, lane, &mma_bar[warp >> 2]);
+    grp.bar_id = 1 + (warp >> 2);
+    const uint32_t tmem_base = tmem_base_s;
+    volatile int* my_slot = &tmem_slot_of[warp >> 2];
+    auto tmem_begin = [&] { if constexpr (kShareSlots) tc::group_acquire(grp, &tmem_free_mask, my_slot, tmem_base, warp & 3); };
+    auto tmem_end = [&] { if constexpr (kShareSlots) tc::group_release(grp, &tmem_free_mask, my_slot); };
 
     float* scratch = sm + S::scratch + warp * S::per_warp;
     float* binsA = scratch + S::s_bins;
@@ -629,13 +647,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         // ---- stage 0: uniform bins linspace(0,1,129) (renderer.py:262-266; i/128 is exact) ------
         for (int j = lane; j <= kMaxT; j += 32) binsA[j] = (float)j * (1.0f / kMaxT);
         __syncwarp();
-        proposal_stage<128, PL, GL, HG>(p, 0, sm, grp, r, binsA, ds, lane);
+        proposal_stage<128, PL, GL, HG>(p, 0, sm, grp, &tmem_free_mask, my_slot, tmem_base, warp & 3, r, binsA, ds, lane);
         weights_from_ds<128>(ds, lane, last_opaque);
         __syncwarp();
         sample_pdf_warp<128, 65>(ds, binsA, cdf, u65, binsB, lane, (p.inds0 && active) ? p.inds0 + 65 * (size_t)ray : nullptr);
 
         // ---- stage 1 -----------------------------------------------------------------------------
-        proposal_stage<64, PL, GL, HG>(p, 1, sm, grp, r, binsB, ds, lane);
+        proposal_stage<64, PL, GL, HG>(p, 1, sm, grp, &tmem_free_mask, my_slot, tmem_base, warp & 3, r, binsB, ds, lane);
         weights_from_ds<64>(ds, lane, last_opaque);
         __syncwarp();
         sample_pdf_warp<64, 33>(ds, binsB, cdf, u33, binsA, lane, (p.inds1 && active) ? p.inds1 + 33 * (size_t)ray : nullptr);
@@ -650,11 +668,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             gather_levels<GL, 2>(p.grid, x01, inside, feat);
             // grid_mlp 2L -> Hg -> Hg -> 16 (ReLU, no bias; network.py:94) on the tensor core: the 4 warps of the group put
             // their 4 x 32 samples into the 128 TMEM lanes, tcgen05.mma (3xTF32 split precision) does the three layers
+            tmem_begin();
             float h1[HG];
             tc::group_layer<2 * GL, HG, true>(grp, sm + S::grid_w0, sm + S::grid_w0 + HG * S::GK, feat, h1);
             float h2[HG];
             tc::group_layer<HG, HG, true>(grp, sm + S::grid_w1, sm + S::grid_w1 + HG * HG, h1, h2);
             tc::group_layer<HG, 16, false>(grp, sm + S::grid_w2, sm + S::grid_w2 + 16 * HG, h2, f16);
+            tmem_end();
         }
         const float sigma = expf(f16[0]);
         ds[home] = __fmul_rn(delta, sigma);

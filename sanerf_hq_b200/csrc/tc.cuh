@@ -182,6 +182,38 @@ __device__ __forceinline__ Group make_group(uint32_t tmem_base, int group, int w
     return g;
 }
 
+// ---- TMEM slots ---------------------------------------------------------------------------------------------------------
+// A CTA with more than 4 groups time-shares the four 128-column slots of its tensor memory: a group holds a slot only for the
+// duration of its tensor-core rounds (a small fraction of a ray's time).  `free_mask` (shared memory) has bit s set when slot
+// s is free.  acquire / release are executed by all 128 threads of the group.
+__device__ __forceinline__ void group_acquire(Group& g, unsigned int* free_mask, volatile int* slot_bcast, uint32_t tmem_base, int warp_in_group) {
+    if (g.issuer) {
+        int s;
+        for (;;) {
+            const unsigned int m = *reinterpret_cast<volatile unsigned int*>(free_mask);
+            if (m) {
+                s = __ffs(m) - 1;
+                if (atomicAnd(free_mask, ~(1u << s)) & (1u << s)) break;
+            } else {
+                __nanosleep(100);
+            }
+        }
+        *slot_bcast = s;
+    }
+    named_barrier(g.bar_id, 128);            // publishes the slot to the group (bar.sync orders shared-memory accesses)
+    const int s = *slot_bcast;
+    g.a_mma = tmem_base + s * kGroupCols;
+    g.d_mma = g.a_mma + kACols;
+    g.a_rw = g.a_mma + ((uint32_t)(warp_in_group * 32) << 16);
+    g.d_rw = g.d_mma + ((uint32_t)(warp_in_group * 32) << 16);
+    fence_after_sync();                      // the previous owner's TMEM reads were ordered before its release
+}
+__device__ __forceinline__ void group_release(Group& g, unsigned int* free_mask, volatile int* slot_bcast) {
+    fence_before_sync();                     // this thread's tcgen05.ld have completed (tmem_ld_wait)
+    named_barrier(g.bar_id, 128);
+    if (g.issuer) atomicOr(free_mask, 1u << *slot_bcast);
+}
+
 // write hi (PART 0) or lo (PART 1) parts of a[K] into K consecutive TMEM columns, 8/16 columns per instruction so that
 // only one chunk of converted values is live at a time
 template <int K, int PART>
