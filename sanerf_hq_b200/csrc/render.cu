@@ -607,7 +607,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 
     const uint32_t total_warps = gridDim.x * kWarps;
     // every warp of the CTA runs the same number of iterations (the groups synchronise inside); a warp past the end
-    // re-renders the last ray and skips the stores
+    // re-renders the last ray and skips the stores.  Rays are dealt to the CTAs round-robin, 16 at a time: at any moment the
+    // whole GPU works on the same ~3 image rows, which keeps the cells they share hot in L2 (measured: giving each CTA one
+    // contiguous block of rays instead costs +2 % on the RGB frame and +35 % on the SAM frame, whose 160 MiB table overflows L2)
     for (uint32_t base = blockIdx.x * kWarps; base < p.N; base += total_warps) {
         const bool active = base + warp < p.N;
         const uint32_t ray = active ? base + warp : p.N - 1;
