@@ -47,10 +47,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     do {
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"   // suspend-time hint: sleep in hardware, do not spin
             "selp.u32 %0, 1, 0, p;\n\t}"
             : "=r"(done)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(20000u)
             : "memory");
     } while (!done);
 }
@@ -264,12 +264,29 @@ __device__ __forceinline__ void group_layer(Group& g, const float* s_hi, const f
             issue_layer<N, K / 8>(d_mma, a_mma + K, s_hi, 1u);
         });
     } else {
-        st_split<K, 0>(g.a_rw, a);
+        // hi pass: write tf32(a) and keep the exact residual a - tf32(a) for the lo pass (3 instead of 4 conversions per value)
+        float res[K];
+#pragma unroll
+        for (int c = 0; c < K; c += 16) {
+            uint32_t t[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) {
+                t[i] = tf32_hi(a[c + i]);
+                res[c + i] = a[c + i] - __uint_as_float(t[i]);
+            }
+            tmem_st16(g.a_rw + c, t);
+        }
         group_round(g, [&] {
             issue_layer<N, K / 8>(d_mma, a_mma, s_hi, 0u);
             issue_layer<N, K / 8>(d_mma, a_mma, s_lo, 1u);
         });
-        st_split<K, 1>(g.a_rw, a);
+#pragma unroll
+        for (int c = 0; c < K; c += 16) {
+            uint32_t t[16];
+#pragma unroll
+            for (int i = 0; i < 16; i++) t[i] = tf32_hi(res[c + i]);
+            tmem_st16(g.a_rw + c, t);
+        }
         group_round(g, [&] { issue_layer<N, K / 8>(d_mma, a_mma, s_hi, 1u); });
     }
 #pragma unroll
