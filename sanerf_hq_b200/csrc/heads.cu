@@ -35,13 +35,11 @@ constexpr int kOff1 = kNCh0 * kImg0, kOff2 = kOff1 + kNCh1 * kImg1, kImgTotal = 
 constexpr int kStageBytes = kImg1 * 2;  // 65536
 constexpr uint32_t kColsAlo = 128, kColsD = 256;
 
-// element index (bf16 units) inside an [N x Kc] K-major no-swizzle operand image: core matrix = 8 n x 8 k (16 B per row)
-__host__ __device__ constexpr int img_index(int n, int k, int N) { return ((k >> 3) * N + n) * 8 + (k & 7); }
-
-__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-    hi = __float2bfloat16_rn(v);
-    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
-}
+using tc::idesc_bf16;
+using tc::mma_bf16_ts;
+using tc::pack_split16;
+using tc::split_bf16;
+__host__ __device__ constexpr int img_index(int n, int k, int N) { return tc::bf16_img_index(n, k, N); }
 
 // ---- prepare: nn.Linear weights -> chunked operand images -------------------------------------------------------
 __global__ void mask_prepare_kernel(const float* __restrict__ w0, const float* __restrict__ w1, const float* __restrict__ w2, uint32_t n_inst,
@@ -70,18 +68,6 @@ __global__ void mask_prepare_kernel(const float* __restrict__ w0, const float* _
     }
 }
 
-// ---- tensor-core helpers (kind::f16, bf16 operands, A from TMEM) -----------------------------------------------------
-__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
-}
-__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
 // one K-chunk of a layer: for every 16-wide k-step the three split-precision products
 //   a_col: first A column of the chunk (hi part; the lo part sits kColsAlo columns further)
 template <int N, int KC>
@@ -103,18 +89,6 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
-// 16 fp32 activations -> 8 columns of bf16 hi pairs + 8 columns of bf16 lo pairs (k even in the low half)
-__device__ __forceinline__ void pack_split16(const float (&v)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[2 * i], h0, l0);
-        split_bf16(v[2 * i + 1], h1, l1);
-        hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-    }
-}
 
 __global__ void __launch_bounds__(kHeadThreads, 1)
     mask_mlp_kernel(const float* __restrict__ mask_in, const float* __restrict__ weights, const __nv_bfloat16* __restrict__ img,

@@ -368,9 +368,9 @@ struct Smem {
     static constexpr int prop_w1 = prop_w0 + 4 * 16 * PKP;   // [2][16]
     // grid_mlp weights as tensor-core operand images (tc.cuh: K-major core matrices), tf32 hi part then lo part
     static constexpr int grid_w0 = (prop_w1 + 2 * 16 + 31) & ~31;  // 2 x [HG][GK]   (128-byte aligned)
-    static constexpr int grid_w1 = grid_w0 + 2 * HG * GK;          // 2 x [HG][HG]
-    static constexpr int grid_w2 = grid_w1 + 2 * HG * HG;          // 2 x [16][HG]
-    static constexpr int view_w0 = grid_w2 + 2 * 16 * HG;          // [32][VP]  (rows >= Hv zero)
+    static constexpr int grid_w1 = grid_w0 + 2 * HG * GK;          // hidden layers: bf16 hi + lo images, 2 x [HG][HG] bf16
+    static constexpr int grid_w2 = grid_w1 + HG * HG;              // 2 x [16][HG] bf16
+    static constexpr int view_w0 = grid_w2 + 16 * HG;              // [32][VP]  (rows >= Hv zero)
     static constexpr int view_w1 = view_w0 + 32 * VP;        // [32][VP]
     static constexpr int view_w2 = view_w1 + 32 * VP;        // [3][32]
     static constexpr int utab = view_w2 + 3 * 32;            // u65 (68 slots) + u33 (36 slots)
@@ -393,8 +393,12 @@ __device__ void stage_weights(float* sm, const RenderParams& p) {
                                                    p.prop_w0[e], tid, kThreads);
     for (int i = tid; i < 32; i += kThreads) sm[S::prop_w1 + i] = __ldg(p.prop_w1[i / 16] + (i % 16));
     tc::stage_split_weights<HG, S::GK, S::GK>(sm + S::grid_w0, sm + S::grid_w0 + HG * S::GK, p.grid_w[0], tid, kThreads);
-    tc::stage_split_weights<HG, HG, HG>(sm + S::grid_w1, sm + S::grid_w1 + HG * HG, p.grid_w[1], tid, kThreads);
-    tc::stage_split_weights<16, HG, HG>(sm + S::grid_w2, sm + S::grid_w2 + 16 * HG, p.grid_w[2], tid, kThreads);
+    {
+        __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(sm + S::grid_w1);
+        __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(sm + S::grid_w2);
+        tc::stage_split_weights_bf16<HG, HG>(w1, w1 + HG * HG, p.grid_w[1], tid, kThreads);
+        tc::stage_split_weights_bf16<16, HG>(w2, w2 + 16 * HG, p.grid_w[2], tid, kThreads);
+    }
     tc::fence_proxy_async_smem();  // the tensor core reads these through the async proxy
     for (int i = tid; i < 32 * S::VP; i += kThreads) {
         const int n = i / S::VP, k = i % S::VP;
@@ -666,16 +670,58 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         const bool inside = sample_point(r, binsA[home], binsA[home + 1], tmid, delta, x01);
         float f16[16];  // grid_mlp output: [0] log-density, [1..15] geo_feat
         {
-            float feat[2 * GL];
-            gather_levels<GL, 2>(p.grid, x01, inside, feat);
-            // grid_mlp 2L -> Hg -> Hg -> 16 (ReLU, no bias; network.py:94) on the tensor core: the 4 warps of the group put
-            // their 4 x 32 samples into the 128 TMEM lanes, tcgen05.mma (3xTF32 split precision) does the three layers
+            // grid_mlp 2L -> Hg -> Hg -> 16 (ReLU, no bias; network.py:94) on the tensor core.  The 4 warps of the group put their
+            // 4 x 32 samples into the 128 TMEM lanes.  The hash-grid features stream into the A operand as they are gathered
+            // (tf32 hi | lo, 3xTF32 for the first layer); the two hidden layers never leave tensor memory
+            // (tc::group_layer_from_tmem, bf16 hi | lo split operands); only the 16 outputs come back to registers.
+            constexpr int GK = 2 * GL;
+            constexpr int LB = GL % 4 == 0 ? 4 : GL;   // levels per tcgen05.st block (8 columns)
+            static_assert(LB == 4, "grid levels come in blocks of 4");
             tmem_begin();
-            float h1[HG];
-            tc::group_layer<2 * GL, HG, true>(grp, sm + S::grid_w0, sm + S::grid_w0 + HG * S::GK, feat, h1);
-            float h2[HG];
-            tc::group_layer<HG, HG, true>(grp, sm + S::grid_w1, sm + S::grid_w1 + HG * HG, h1, h2);
-            tc::group_layer<HG, 16, false>(grp, sm + S::grid_w2, sm + S::grid_w2 + 16 * HG, h2, f16);
+            {
+                LevelLoads buf[2];
+                level_issue(p.grid, 0, x01, buf[0]);
+                if (GL > 1) level_issue(p.grid, 1, x01, buf[1]);
+                uint32_t hi[8], lo[8];
+#pragma unroll
+                for (int l = 0; l < GL; l++) {
+                    float o0, o1;
+                    level_finish(buf[l % 2], o0, o1);
+                    if (l + 2 < GL) level_issue(p.grid, l + 2, x01, buf[l % 2]);
+                    o0 = inside ? o0 : 0.f;
+                    o1 = inside ? o1 : 0.f;
+                    const int c = 2 * (l % 4);
+                    hi[c] = tc::tf32_hi(o0);
+                    lo[c] = tc::tf32_lo(o0, hi[c]);
+                    hi[c + 1] = tc::tf32_hi(o1);
+                    lo[c + 1] = tc::tf32_lo(o1, hi[c + 1]);
+                    if (l % 4 == 3) {
+                        tc::tmem_st8(grp.a_rw + 2 * (l - 3), hi);
+                        tc::tmem_st8(grp.a_rw + GK + 2 * (l - 3), lo);
+                    }
+                }
+            }
+            {
+                const uint32_t d_mma = grp.d_mma, a_mma = grp.a_mma;
+                const float* w0h = sm + S::grid_w0;
+                const float* w0l = w0h + HG * GK;
+                tc::group_round(grp, [&] {
+                    tc::issue_layer<HG, GK / 8>(d_mma, a_mma, w0h, 0u);
+                    tc::issue_layer<HG, GK / 8>(d_mma, a_mma, w0l, 1u);
+                    tc::issue_layer<HG, GK / 8>(d_mma, a_mma + GK, w0h, 1u);
+                });
+            }
+            const __nv_bfloat16* w1 = reinterpret_cast<const __nv_bfloat16*>(sm + S::grid_w1);
+            const __nv_bfloat16* w2 = reinterpret_cast<const __nv_bfloat16*>(sm + S::grid_w2);
+            tc::group_layer_from_tmem<HG, HG>(grp, w1, w1 + HG * HG);
+            tc::group_layer_from_tmem<HG, 16>(grp, w2, w2 + 16 * HG);
+            {
+                uint32_t t[16];
+                tc::tmem_ld16(grp.d_rw, t);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; i++) f16[i] = __uint_as_float(t[i]);
+            }
             tmem_end();
         }
         const float sigma = expf(f16[0]);

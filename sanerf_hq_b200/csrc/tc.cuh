@@ -11,6 +11,7 @@
 // representable in tf32),  D = Ah*Wh + Ah*Wl + Al*Wh  with fp32 accumulation in the tensor core; the dropped
 // Al*Wl term is 2^-22 relative.
 #pragma once
+#include <cuda_bf16.h>
 #include <stdint.h>
 
 namespace sanerf {
@@ -333,6 +334,89 @@ __device__ __forceinline__ void group_layer_x2(Group& g, const float* s_hi, cons
             else d1[c + i - N] = RELU ? fmaxf(v, 0.f) : v;
         }
     }
+}
+
+// ================================================================================================================
+// bf16 split-precision layers (kind::f16): a = hi + lo with two bf16 (16 significant bits, 2^-18 relative), two K values per
+// 32-bit TMEM column, so a K-wide layer needs K/2 + K/2 columns of A: a 64-wide hidden layer fits the 64-column A region with
+// BOTH parts resident -> one round per layer and no activation ever waits in registers.  Used for the hidden layers of
+// grid_mlp (whose outputs feed exp() and the compositing, not the index buffers) and for the 256-wide heads (heads.cu).
+// ================================================================================================================
+__device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+    hi = __float2bfloat16_rn(v);
+    lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+}
+// 16 fp32 values -> 8 columns of bf16 hi pairs + 8 columns of bf16 lo pairs (even k in the low half of the column)
+__device__ __forceinline__ void pack_split16(const float (&v)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v[2 * i], h0, l0);
+        split_bf16(v[2 * i + 1], h1, l1);
+        hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+}
+// element index (bf16 units) inside an [N x K] K-major no-swizzle operand image: core matrix = 8 n x 8 k (16 B per row)
+__host__ __device__ constexpr int bf16_img_index(int n, int k, int N) { return ((k >> 3) * N + n) * 8 + (k & 7); }
+__host__ __device__ constexpr uint32_t idesc_bf16(uint32_t M, uint32_t N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// W [N,K] fp32 (nn.Linear layout) -> bf16 hi / lo operand images in shared memory (each N*K bf16)
+template <int N, int K>
+__device__ __forceinline__ void stage_split_weights_bf16(__nv_bfloat16* s_hi, __nv_bfloat16* s_lo, const float* __restrict__ w, int tid, int nthreads) {
+    static_assert(K % 16 == 0, "bf16 MMA K step");
+    for (int i = tid; i < N * K; i += nthreads) {
+        const int n = i / K, k = i % K;
+        __nv_bfloat16 h, l;
+        split_bf16(__ldg(w + i), h, l);
+        s_hi[bf16_img_index(n, k, N)] = h;
+        s_lo[bf16_img_index(n, k, N)] = l;
+    }
+}
+// D[128,N] = A[128,K] * W^T with the three split products per 16-wide k-step; A hi at a_col, A lo at a_col + K/2
+template <int N, int K>
+__device__ __forceinline__ void issue_layer_bf16(uint32_t d_tmem, uint32_t a_col, const __nv_bfloat16* s_hi, const __nv_bfloat16* s_lo) {
+    constexpr uint32_t idesc = idesc_bf16(128, N);
+    const uint32_t wh = smem_u32(s_hi), wl = smem_u32(s_lo);
+#pragma unroll
+    for (int j = 0; j < K / 16; j++) {
+        const uint64_t bh = smem_desc_kmajor(wh + j * 2 * 16 * N, 16 * N, 128);
+        const uint64_t bl = smem_desc_kmajor(wl + j * 2 * 16 * N, 16 * N, 128);
+        mma_bf16_ts(d_tmem, a_col + 8 * j, bh, idesc, j > 0 ? 1u : 0u);
+        mma_bf16_ts(d_tmem, a_col + 8 * j, bl, idesc, 1u);
+        mma_bf16_ts(d_tmem, a_col + K / 2 + 8 * j, bh, idesc, 1u);
+    }
+}
+// Hidden layer fed from tensor memory: the previous layer's pre-activations sit in the D region (K fp32 columns per row);
+// each thread streams its row 16 columns at a time through ReLU + bf16 split into the A region, then one round of MMAs
+// overwrites the D region with this layer's pre-activations.  Nothing but a 16-value chunk is ever live in registers.
+template <int K, int N>
+__device__ __forceinline__ void group_layer_from_tmem(Group& g, const __nv_bfloat16* s_hi, const __nv_bfloat16* s_lo) {
+    static_assert(K % 16 == 0 && K <= (int)kACols && N % 16 == 0 && N <= 64, "layer shape");
+#pragma unroll
+    for (int c = 0; c < K; c += 16) {
+        uint32_t t[16];
+        tmem_ld16(g.d_rw + c, t);
+        tmem_ld_wait();
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; i++) v[i] = fmaxf(__uint_as_float(t[i]), 0.f);
+        uint32_t hi[8], lo[8];
+        pack_split16(v, hi, lo);
+        tmem_st8(g.a_rw + c / 2, hi);
+        tmem_st8(g.a_rw + K / 2 + c / 2, lo);
+    }
+    const uint32_t d_mma = g.d_mma, a_mma = g.a_mma;
+    group_round(g, [&] { issue_layer_bf16<N, K>(d_mma, a_mma, s_hi, s_lo); });
 }
 
 }  // namespace tc
