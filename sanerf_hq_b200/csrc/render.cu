@@ -415,10 +415,9 @@ __device__ void stage_weights(float* sm, const RenderParams& p) {
 
 // weights of one stage from delta*sigma (renderer.py:308-325); ds[] (shared, per warp) is
 // overwritten with the weights.  T samples, sample j = lane + 32*i.
-template <int T>
-__device__ __forceinline__ void weights_from_ds(float* ds, int lane, bool last_opaque) {
+__device__ __forceinline__ void weights_from_ds(float* ds, int T, int lane, bool last_opaque) {
     float carry = 0.f;
-#pragma unroll
+#pragma unroll 1
     for (int i = 0; i < T / 32; i++) {
         const int j = lane + 32 * i;
         const float v = ds[j];
@@ -436,28 +435,31 @@ __device__ __forceinline__ void weights_from_ds(float* ds, int lane, bool last_o
 
 // sample_pdf (renderer.py:84-119), perturb=False.  w[] = T0 weights, bins[] = T0+1 bins (shared);
 // writes TN new bins; cdf[] is scratch (T0+1).  u = linspace(.5/TN, 1-.5/TN, TN) table (shared).
-template <int T0, int TN>
-__device__ __forceinline__ void sample_pdf_warp(const float* w, const float* bins, float* cdf, const float* u, float* out, int lane,
-                                                int16_t* inds_out) {
-    constexpr int PER = T0 / 32;
-    float wp[PER];
+// T0 (<= 128) and TN are runtime values so that ONE copy of this code serves both resampling steps.
+__device__ __forceinline__ void sample_pdf_warp(const float* w, const float* bins, float* cdf, const float* u, float* out, int T0, int TN,
+                                                int lane, int16_t* inds_out) {
+    const int per = T0 / 32;                   // <= 4
+    float wp[4];
     float part = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; i++) {
-        wp[i] = w[lane + 32 * i] + 0.01f;
-        part += wp[i];
+    for (int i = 0; i < 4; i++) {
+        wp[i] = i < per ? w[lane + 32 * i] + 0.01f : 0.f;
+        if (i < per) part += wp[i];
     }
     const float total = warp_sum(part);
     float carry = 0.f;
     if (lane == 0) cdf[0] = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER; i++) {
-        const float pdf = __fdiv_rn(wp[i], total);
-        const float incl = warp_inclusive_scan(pdf, lane) + carry;
-        carry = __shfl_sync(kFull, incl, 31);
-        cdf[lane + 32 * i + 1] = fminf(incl, 1.0f);
+    for (int i = 0; i < 4; i++) {
+        if (i < per) {                         // uniform
+            const float pdf = __fdiv_rn(wp[i], total);
+            const float incl = warp_inclusive_scan(pdf, lane) + carry;
+            carry = __shfl_sync(kFull, incl, 31);
+            cdf[lane + 32 * i + 1] = fminf(incl, 1.0f);
+        }
     }
     __syncwarp();
+#pragma unroll 1
     for (int k = lane; k < TN; k += 32) {
         const float uk = u[k];
         int lo = 0, hi = T0 + 1;               // searchsorted(cdf, u, right=True): #entries <= u
@@ -528,8 +530,8 @@ __device__ __forceinline__ bool sample_point(const RayCtx& r, float b0, float b1
 }
 
 // proposal stage: T samples through proposal network e; fills ds[] with delta*sigma
-template <int T, int PL, int GL, int HG>
-__device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, const float* sm, tc::Group& grp, unsigned int* free_mask,
+template <int PL, int GL, int HG>
+__device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, int T, const float* sm, tc::Group& grp, unsigned int* free_mask,
                                                volatile int* my_slot, uint32_t tmem_base, int warp_in_group, const RayCtx& r,
                                                const float* bins, float* ds, int lane) {
     using S = Smem<PL, GL, HG>;
@@ -546,7 +548,7 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, con
         float feata[S::PKP], featb[S::PKP];
         {
             float fa[2 * PL], fb[2 * PL];
-            gather_levels_x2<PL, 2>(g, xa, xb, ina, inb, fa, fb);
+            gather_levels_x2<PL, (kWarps > 16 ? 1 : 2)>(g, xa, xb, ina, inb, fa, fb);
 #pragma unroll
             for (int k = 0; k < S::PKP; k++) {
                 feata[k] = k < 2 * PL ? fa[k] : 0.f;
@@ -653,16 +655,22 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         // ---- stage 0: uniform bins linspace(0,1,129) (renderer.py:262-266; i/128 is exact) ------
         for (int j = lane; j <= kMaxT; j += 32) binsA[j] = (float)j * (1.0f / kMaxT);
         __syncwarp();
-        proposal_stage<128, PL, GL, HG>(p, 0, sm, grp, &tmem_free_mask, my_slot, tmem_base, warp & 3, r, binsA, ds, lane);
-        weights_from_ds<128>(ds, lane, last_opaque);
-        __syncwarp();
-        sample_pdf_warp<128, 65>(ds, binsA, cdf, u65, binsB, lane, (p.inds0 && active) ? p.inds0 + 65 * (size_t)ray : nullptr);
-
-        // ---- stage 1 -----------------------------------------------------------------------------
-        proposal_stage<64, PL, GL, HG>(p, 1, sm, grp, &tmem_free_mask, my_slot, tmem_base, warp & 3, r, binsB, ds, lane);
-        weights_from_ds<64>(ds, lane, last_opaque);
-        __syncwarp();
-        sample_pdf_warp<64, 33>(ds, binsB, cdf, u33, binsA, lane, (p.inds1 && active) ? p.inds1 + 33 * (size_t)ray : nullptr);
+        // one copy of the proposal-stage code serves both stages (runtime network index / sample count): the ray loop is
+        // instruction-fetch sensitive, so its SASS footprint matters
+        {
+            float* bin_in = binsA;
+            float* bin_out = binsB;
+#pragma unroll 1
+            for (int st = 0; st < 2; st++) {
+                const int T = st ? kMaxT / 2 : kMaxT, TN = T / 2 + 1;
+                proposal_stage<PL, GL, HG>(p, st, T, sm, grp, &tmem_free_mask, my_slot, tmem_base, warp & 3, r, bin_in, ds, lane);
+                weights_from_ds(ds, T, lane, last_opaque);
+                __syncwarp();
+                int16_t* tap = st ? p.inds1 : p.inds0;
+                sample_pdf_warp(ds, bin_in, cdf, st ? u33 : u65, bin_out, T, TN, lane, (tap && active) ? tap + TN * (size_t)ray : nullptr);
+                float* t = bin_in; bin_in = bin_out; bin_out = t;
+            }
+        }   // after two swaps the final-stage bins are in binsA again
 
         // ---- stage 2: the radiance field, one sample per lane -----------------------------------
         float tmid, delta, x01[3];
@@ -679,26 +687,32 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             static_assert(LB == 4, "grid levels come in blocks of 4");
             tmem_begin();
             {
-                LevelLoads buf[2];
-                level_issue(p.grid, 0, x01, buf[0]);
-                if (GL > 1) level_issue(p.grid, 1, x01, buf[1]);
-                uint32_t hi[8], lo[8];
+                LevelLoads buf0, buf1;             // levels 4*lb and 4*lb+1 are in flight at the top of each iteration
+                level_issue(p.grid, 0, x01, buf0);
+                level_issue(p.grid, 1, x01, buf1);
+#pragma unroll 1
+                for (int lb = 0; lb < GL / 4; lb++) {
+                    uint32_t hi[8], lo[8];
 #pragma unroll
-                for (int l = 0; l < GL; l++) {
-                    float o0, o1;
-                    level_finish(buf[l % 2], o0, o1);
-                    if (l + 2 < GL) level_issue(p.grid, l + 2, x01, buf[l % 2]);
-                    o0 = inside ? o0 : 0.f;
-                    o1 = inside ? o1 : 0.f;
-                    const int c = 2 * (l % 4);
-                    hi[c] = tc::tf32_hi(o0);
-                    lo[c] = tc::tf32_lo(o0, hi[c]);
-                    hi[c + 1] = tc::tf32_hi(o1);
-                    lo[c + 1] = tc::tf32_lo(o1, hi[c + 1]);
-                    if (l % 4 == 3) {
-                        tc::tmem_st8(grp.a_rw + 2 * (l - 3), hi);
-                        tc::tmem_st8(grp.a_rw + GK + 2 * (l - 3), lo);
+                    for (int j = 0; j < 4; j++) {
+                        const int l = 4 * lb + j;
+                        float o0, o1;
+                        if (j % 2 == 0) {
+                            level_finish(buf0, o0, o1);
+                            if (l + 2 < GL) level_issue(p.grid, l + 2, x01, buf0);
+                        } else {
+                            level_finish(buf1, o0, o1);
+                            if (l + 2 < GL) level_issue(p.grid, l + 2, x01, buf1);
+                        }
+                        o0 = inside ? o0 : 0.f;
+                        o1 = inside ? o1 : 0.f;
+                        hi[2 * j] = tc::tf32_hi(o0);
+                        lo[2 * j] = tc::tf32_lo(o0, hi[2 * j]);
+                        hi[2 * j + 1] = tc::tf32_hi(o1);
+                        lo[2 * j + 1] = tc::tf32_lo(o1, hi[2 * j + 1]);
                     }
+                    tc::tmem_st8(grp.a_rw + 8 * lb, hi);
+                    tc::tmem_st8(grp.a_rw + GK + 8 * lb, lo);
                 }
             }
             {
@@ -727,7 +741,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         const float sigma = expf(f16[0]);
         ds[home] = __fmul_rn(delta, sigma);
         __syncwarp();
-        weights_from_ds<32>(ds, lane, last_opaque);
+        weights_from_ds(ds, 32, lane, last_opaque);
         __syncwarp();
         const float w = ds[home];
         __syncwarp();
@@ -883,7 +897,7 @@ __global__ void __launch_bounds__(256) sample_pdf_kernel(const float* __restrict
     for (int j = lane; j < T0; j += 32) s_w[warp][j] = weights[(size_t)ray * T0 + j];
     for (int j = lane; j <= T0; j += 32) s_b[warp][j] = bins[(size_t)ray * (T0 + 1) + j];
     __syncwarp();
-    sample_pdf_warp<T0, TN>(s_w[warp], s_b[warp], s_c[warp], s_u, s_o[warp], lane, inds ? inds + (size_t)ray * TN : nullptr);
+    sample_pdf_warp(s_w[warp], s_b[warp], s_c[warp], s_u, s_o[warp], T0, TN, lane, inds ? inds + (size_t)ray * TN : nullptr);
     for (int k = lane; k < TN; k += 32) new_bins[(size_t)ray * TN + k] = s_o[warp][k];
 }
 

@@ -387,7 +387,7 @@ template <int N, int K>
 __device__ __forceinline__ void issue_layer_bf16(uint32_t d_tmem, uint32_t a_col, const __nv_bfloat16* s_hi, const __nv_bfloat16* s_lo) {
     constexpr uint32_t idesc = idesc_bf16(128, N);
     const uint32_t wh = smem_u32(s_hi), wl = smem_u32(s_lo);
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < K / 16; j++) {
         const uint64_t bh = smem_desc_kmajor(wh + j * 2 * 16 * N, 16 * N, 128);
         const uint64_t bl = smem_desc_kmajor(wl + j * 2 * 16 * N, 16 * N, 128);
@@ -402,7 +402,7 @@ __device__ __forceinline__ void issue_layer_bf16(uint32_t d_tmem, uint32_t a_col
 template <int K, int N>
 __device__ __forceinline__ void group_layer_from_tmem(Group& g, const __nv_bfloat16* s_hi, const __nv_bfloat16* s_lo) {
     static_assert(K % 16 == 0 && K <= (int)kACols && N % 16 == 0 && N <= 64, "layer shape");
-#pragma unroll
+#pragma unroll 1
     for (int c = 0; c < K; c += 16) {
         uint32_t t[16];
         tmem_ld16(g.d_rw + c, t);
