@@ -35,8 +35,9 @@ namespace sanerf {
 constexpr int kWarps = SANERF_RENDER_WARPS;   // warps (= rays in flight) per CTA; 4 warps = one tensor-core group
 constexpr int kGroups = kWarps / 4;
 constexpr bool kShareSlots = kGroups > 4;     // more groups than 128-column TMEM slots: time-share them (tc::group_acquire).
-// Measured on B200: 20 warps (96 registers, slot sharing) = 19.1 ms per 800x800 frame vs 13.7 ms for 16 warps (128 registers):
-// the extra spills cost more than the extra warps hide.
+// Measured on B200 (800x800 RGB frame): 16 warps / 128 registers 12.81 ms; 20 warps / 96 registers 12.82 ms; 24 warps / 80
+// registers 13.1 ms -- more resident warps lower the L1 hit rate (90 % -> 83 %) as fast as they hide latency, so the default
+// stays at 16 (no slot sharing, no spills).
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxT = 128;              // samples of the widest stage
 constexpr unsigned kFull = 0xffffffffu;
