@@ -136,6 +136,14 @@ __device__ __forceinline__ void contract3(float& x, float& y, float& z) {
     z = __fmul_rn(z, idx == 2 ? big : inv);
 }
 
+// floor of a clamped grid coordinate 0 <= pos < 2^22 without the conversion unit (FRND / F2I run on the quarter-rate XU pipe):
+// pos + 2^23 rounded toward zero has an ulp of 1, so its low mantissa bits ARE floor(pos); both results are exact.
+__device__ __forceinline__ void floor_split(float pos, uint32_t& cell, float& frac) {
+    const float t = __fadd_rz(pos, 8388608.0f);
+    cell = __float_as_uint(t) & 0x007fffffu;
+    frac = pos - (t - 8388608.0f);
+}
+
 // One level of a C-channel grid at a point in [0,1]^3: same arithmetic as grid_encode.cu / the
 // reference kernel (gridencoder.cu:140-195) with the per-level constants taken from GridDev.
 template <int C>
@@ -149,10 +157,8 @@ __device__ __forceinline__ void encode_level(const GridDev& g, int l, const floa
 #pragma unroll
     for (int d = 0; d < 3; d++) {
         float pos = fminf(fmaxf(__fmaf_rn(x[d], resf, -0.5f), 0.0f), top);
-        const float fl = floorf(pos);
-        b0[d] = (uint32_t)fl;
+        floor_split(pos, b0[d], f[d]);
         b1[d] = min(b0[d] + 1, res - 1);
-        f[d] = pos - fl;
     }
     uint32_t row[8];
     float w[8];
@@ -221,10 +227,8 @@ __device__ __forceinline__ void level_issue(const GridDev& g, int l, const float
 #pragma unroll
     for (int d = 0; d < 3; d++) {
         float pos = fminf(fmaxf(__fmaf_rn(x[d], resf, -0.5f), 0.0f), top);
-        const float fl = floorf(pos);
-        b0[d] = (uint32_t)fl;
+        floor_split(pos, b0[d], o.f[d]);
         b1[d] = min(b0[d] + 1, res - 1);
-        o.f[d] = pos - fl;
     }
     if (hmask == 0) {  // dense level: x + y*res + z*res^2 < rows, no modulo needed
         const uint32_t y0 = b0[1] * res, y1 = b1[1] * res, z0 = b0[2] * res * res, z1 = b1[2] * res * res;
@@ -309,10 +313,8 @@ __device__ __forceinline__ void quarter_level(const GridDev& g, int l, const flo
 #pragma unroll
     for (int d = 0; d < 3; d++) {
         float pos = fminf(fmaxf(__fmaf_rn(x[d], resf, -0.5f), 0.0f), top);
-        const float fl = floorf(pos);
-        b0[d] = (uint32_t)fl;
+        floor_split(pos, b0[d], f[d]);
         b1[d] = min(b0[d] + 1, res - 1);
-        f[d] = pos - fl;
     }
     float2 v[8];
     if (hmask == 0) {
