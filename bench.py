@@ -314,7 +314,7 @@ def main():
         achieved = BYTES_PER_RAY[wl] * n_local / (k_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get(wl)
+            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get(wl)   # from the committed ncu capture
         except Exception:
             pass
         line = {
@@ -322,12 +322,15 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{wl} {H}x{W} per GPU (global frame {H * world}x{W}), hashgrid L=16 T=2^19, MLP 2x64, "
-                                   f"samples 128+64+32, one fused launch per frame (reference: 4096 rays/batch)",
+                                   f"samples 128+64+32, one fused render launch per frame (reference: 4096 rays/batch)",
                        "rays_per_step": n_total, "poses": n_res, "parallelism": f"ray-row sharding x{world} + 1 all-gather",
                        "l2": "no flush" if flush is None else "L2 flushed between timed steps (256 MiB fill, outside the step events)",
                        "weights": "random init: seed-0 constructor, hash tables U(-1,1)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "sanerf::render_kernel",
+                         "traffic": traffic, "peak_source": peak_src,
+                         "kernel": "sanerf::render_kernel" if wl == "rgb" else
+                                   ("sanerf::render_kernel + sanerf::samvit_mlp_kernel" if wl == "sam" else
+                                    "sanerf::render_kernel + sanerf::mask_mlp_kernel (5 chunks of 131072 rays)"),
                          "kernel_ms": k_ms, "algorithmic_bytes_per_ray": BYTES_PER_RAY[wl],
                          "mlp_tflops": FLOPS_PER_RAY[wl] * n_local / (k_ms * 1e-3) / 1e12},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * n_local * 12 * world,
