@@ -94,19 +94,22 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
     mask_mlp_kernel(const float* __restrict__ mask_in, const float* __restrict__ weights, const __nv_bfloat16* __restrict__ img,
                     float* __restrict__ logits, uint32_t n_tiles, uint32_t n_rays, uint32_t n_inst) {
     extern __shared__ __align__(128) uint8_t smem[];   // [2 stages x 64 KB][layer-2 image 16 KB]
-    __shared__ __align__(8) uint64_t bar_free[2], bar_done;
+    __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done, bar_w2;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, part = warp >> 2;
     const uint32_t stage_saddr = tc::smem_u32(smem), w2_saddr = stage_saddr + 2 * kStageBytes;
 
-    // resident layer-2 image + barriers + tensor memory
-    for (int i = tid; i < kImg2 * 2 / 16; i += kHeadThreads) cp_async16(w2_saddr + i * 16, reinterpret_cast<const uint8_t*>(img + kOff2) + i * 16);
-    cp_async_commit();
+    // barriers + tensor memory; the resident layer-2 image arrives by TMA bulk copy
     if (tid == 0) {
-        tc::mbar_init(&bar_free[0], 1);
-        tc::mbar_init(&bar_free[1], 1);
+        for (int i = 0; i < 2; i++) {
+            tc::mbar_init(&bar_full[i], 1);
+            tc::mbar_init(&bar_free[i], 1);
+        }
         tc::mbar_init(&bar_done, 1);
+        tc::mbar_init(&bar_w2, 1);
         tc::fence_mbar_init();
+        tc::mbar_expect_tx(&bar_w2, kImg2 * 2);
+        tc::tma_load_1d(w2_saddr, img + kOff2, kImg2 * 2, &bar_w2);
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
     tc::fence_before_sync();
@@ -116,42 +119,43 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
     const uint32_t a_mma = tm, d_mma = tm + kColsD;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t a_rw = a_mma + lane_base, d_rw = d_mma + lane_base;
-    uint32_t ph_free[2] = {0, 0}, ph_done = 0;
+    uint32_t ph_full[2] = {0, 0}, ph_free[2] = {0, 0}, ph_done = 0;   // ph_full / ph_free are only used by thread 0
 
     const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const uint32_t total_chunks = my_tiles * kChunksPerTile;
-    // chunk g of this CTA's stream -> source image and byte count (the images are the same for every tile)
-    auto load_chunk = [&](uint32_t g) {
+    // Weight ring, driven entirely by thread 0 (which also issues the MMAs): chunk g of this CTA's stream lives in stage g & 1.
+    // TMA bulk copy -> bar_full[stage]; tcgen05.commit of the MMAs that read the stage -> bar_free[stage].
+    auto load_chunk = [&](uint32_t g) {   // thread 0 only
         const uint32_t c = g % kChunksPerTile;
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(c < kNCh0 ? img + c * kImg0 : img + kOff1 + (c - kNCh0) * kImg1);
-        const uint32_t bytes = (c < kNCh0 ? kImg0 : kImg1) * 2, dst = stage_saddr + (g & 1) * kStageBytes;
-        for (uint32_t i = tid; i < bytes / 16; i += kHeadThreads) cp_async16(dst + i * 16, src + i * 16);
-        cp_async_commit();
+        const void* src = c < kNCh0 ? img + c * kImg0 : img + kOff1 + (c - kNCh0) * kImg1;
+        const uint32_t bytes = (c < kNCh0 ? kImg0 : kImg1) * 2;
+        tc::mbar_expect_tx(&bar_full[g & 1], bytes);
+        tc::tma_load_1d(stage_saddr + (g & 1) * kStageBytes, src, bytes, &bar_full[g & 1]);
     };
-    // a chunk is consumed: its MMAs are issued; then the stage the PREVIOUS chunk used is recycled for the NEXT chunk
-    uint32_t g = 0;
-    auto consume = [&](auto&& issue, bool last_of_layer) {
-        cp_async_wait_all();              // chunk g (and, the first time, the layer-2 image) has landed
-        tc::fence_proxy_async_smem();     // cp.async wrote through the generic proxy; the tensor core reads through the async proxy
+    uint32_t g = 0;   // next chunk of the stream (meaningful in thread 0)
+    // One layer (or accumulation phase): everybody's A rows are in TMEM -> thread 0 walks the layer's chunks: wait for the
+    // bytes, issue the MMAs, commit, and refill the stage the previous chunk has released with the chunk after this one.
+    auto run_chunks = [&](int n_chunks, auto&& issue) {
         tc::fence_before_sync();          // this thread's tcgen05.st / tcgen05.ld are ordered before the barrier
         __syncthreads();
         if (tid == 0) {
             tc::fence_after_sync();
-            issue(stage_saddr + (g & 1) * kStageBytes);
-            tc::mma_commit(&bar_free[g & 1]);
-            if (last_of_layer) tc::mma_commit(&bar_done);
+            for (int c = 0; c < n_chunks; c++, g++) {
+                tc::mbar_wait(&bar_full[g & 1], ph_full[g & 1]);
+                ph_full[g & 1] ^= 1;
+                issue(c, stage_saddr + (g & 1) * kStageBytes);
+                tc::mma_commit(&bar_free[g & 1]);
+                if (c == n_chunks - 1) tc::mma_commit(&bar_done);
+                if (g + 1 < total_chunks) {
+                    if (g >= 1) {         // the MMAs of chunk g-1 read stage (g+1) & 1
+                        tc::mbar_wait(&bar_free[(g + 1) & 1], ph_free[(g + 1) & 1]);
+                        ph_free[(g + 1) & 1] ^= 1;
+                    }
+                    load_chunk(g + 1);
+                }
+            }
         }
         __syncwarp();
-        if (g + 1 < total_chunks) {
-            if (g >= 1) {                 // MMAs of chunk g-1 read stage (g+1)&1
-                tc::mbar_wait(&bar_free[(g + 1) & 1], ph_free[(g + 1) & 1]);
-                ph_free[(g + 1) & 1] ^= 1;
-            }
-            load_chunk(g + 1);
-        }
-        g++;
-    };
-    auto wait_layer = [&] {
         tc::mbar_wait(&bar_done, ph_done);
         ph_done ^= 1;
         tc::fence_after_sync();
@@ -177,7 +181,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         tc::tmem_st_wait();
     };
 
-    if (total_chunks) load_chunk(0);
+    if (tid == 0 && total_chunks) load_chunk(0);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- layer-0 input: this thread's row, k in [0,64) (part 0) or [64,144) (part 1) ---------------------------
         const float* src = mask_in + (size_t)tile * kMaskK0 * 128 + q * 32 + lane;
@@ -197,27 +201,24 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         }
         tc::tmem_st_wait();
         // ---- layer 0: 143(+1) -> 256 ------------------------------------------------------------------------------
-#pragma unroll 1
-        for (int c = 0; c < kNCh0; c++)
-            consume([&](uint32_t saddr) { issue_chunk<kMaskH, kCh0>(d_mma, a_mma + c * (kCh0 / 2), saddr, c > 0 ? 1u : 0u); }, c == kNCh0 - 1);
-        wait_layer();
+        run_chunks(kNCh0, [&](int c, uint32_t saddr) { issue_chunk<kMaskH, kCh0>(d_mma, a_mma + c * (kCh0 / 2), saddr, c > 0 ? 1u : 0u); });
         epilogue_to_a();
         // ---- layer 1: 256 -> 256 --------------------------------------------------------------------------------------
-#pragma unroll 1
-        for (int c = 0; c < kNCh1; c++)
-            consume([&](uint32_t saddr) { issue_chunk<kMaskH, kCh1>(d_mma, a_mma + c * (kCh1 / 2), saddr, c > 0 ? 1u : 0u); }, c == kNCh1 - 1);
-        wait_layer();
+        run_chunks(kNCh1, [&](int c, uint32_t saddr) { issue_chunk<kMaskH, kCh1>(d_mma, a_mma + c * (kCh1 / 2), saddr, c > 0 ? 1u : 0u); });
         epilogue_to_a();
         // ---- layer 2: 256 -> n_inst (16 output columns), resident image ----------------------------------------------
         tc::fence_before_sync();
         __syncthreads();
         if (tid == 0) {
             tc::fence_after_sync();
+            if (tile == blockIdx.x) tc::mbar_wait(&bar_w2, 0);   // first use: the resident image has landed
             issue_chunk<kMaskNOut, kMaskH>(d_mma, a_mma, w2_saddr, 0u);
             tc::mma_commit(&bar_done);
         }
         __syncwarp();
-        wait_layer();
+        tc::mbar_wait(&bar_done, ph_done);
+        ph_done ^= 1;
+        tc::fence_after_sync();
         // ---- composite: logits[ray] = sum_samples w * point_masks (renderer.py:384); one warp = one ray ---------------
         if (part == 0) {
             uint32_t t[16];
@@ -252,7 +253,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
 // the cp.async ring.  Layer 2 is two accumulating phases: A = hidden (K=256), then A = the input tile again (K=163 -> 176).
 // The input tile (row-major [128,163] fp32, 83 KB) is staged once in shared memory and used by both phases.
 // =====================================================================================================================
-constexpr int kSamIn = 163, kSamInP = 176, kSamW = 256;
+constexpr int kSamIn = 163, kSamW = 256;   // (the input is padded to 176 = 11 k-steps of 16)
 struct SamChunk {
     uint32_t img_off;   // bf16 elements from the start of the image workspace
     uint16_t kc;        // K of the chunk (48 or 64)
@@ -295,15 +296,16 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
                       const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ b3, const float* __restrict__ b4,
                       const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ out, uint32_t n_tiles, uint32_t n_rays) {
     extern __shared__ __align__(128) uint8_t smem[];   // [2 stages x 64 KB][input tile 128 x 163 fp32]
-    __shared__ __align__(8) uint64_t bar_free[2], bar_done;
+    __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, part = warp >> 2;
     const uint32_t stage_saddr = tc::smem_u32(smem);
     float* xt = reinterpret_cast<float*>(smem + 2 * kStageBytes);
-    const uint32_t xt_saddr = stage_saddr + 2 * kStageBytes;
     if (tid == 0) {
-        tc::mbar_init(&bar_free[0], 1);
-        tc::mbar_init(&bar_free[1], 1);
+        for (int i = 0; i < 2; i++) {
+            tc::mbar_init(&bar_full[i], 1);
+            tc::mbar_init(&bar_free[i], 1);
+        }
         tc::mbar_init(&bar_done, 1);
         tc::fence_mbar_init();
     }
@@ -314,45 +316,43 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
     const uint32_t tm = tmem_base_s, a_mma = tm, d_mma = tm + kColsD;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t a_rw = a_mma + lane_base, d_rw = d_mma + lane_base;
-    uint32_t ph_free[2] = {0, 0}, ph_done = 0;
+    uint32_t ph_full[2] = {0, 0}, ph_free[2] = {0, 0}, ph_done = 0;   // ph_full / ph_free are only used by thread 0
     const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const uint32_t total_chunks = my_tiles * kSamChunks;
     const int row = q * 32 + lane;
 
-    auto load_chunk = [&](uint32_t g) {
+    auto load_chunk = [&](uint32_t g) {   // thread 0 only: TMA bulk copy of chunk g into stage g & 1
         const SamChunk ch = c_sam_chunks[g % kSamChunks];
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(img + ch.img_off);
-        const uint32_t bytes = 2u * kSamW * ch.kc * 2u, dst = stage_saddr + (g & 1) * kStageBytes;
-        for (uint32_t i = tid; i < bytes / 16; i += kHeadThreads) cp_async16(dst + i * 16, src + i * 16);
-        cp_async_commit();
+        const uint32_t bytes = 2u * kSamW * ch.kc * 2u;
+        tc::mbar_expect_tx(&bar_full[g & 1], bytes);
+        tc::tma_load_1d(stage_saddr + (g & 1) * kStageBytes, img + ch.img_off, bytes, &bar_full[g & 1]);
     };
     uint32_t g = 0;
-    // consume the next chunk of the stream (see mask_mlp_kernel::consume)
-    auto consume = [&] {
-        const SamChunk ch = c_sam_chunks[g % kSamChunks];
-        cp_async_wait_all();
-        tc::fence_proxy_async_smem();
+    // one accumulation phase of n_chunks chunks (see mask_mlp_kernel::run_chunks)
+    auto run_chunks = [&](int n_chunks) {
         tc::fence_before_sync();
         __syncthreads();
         if (tid == 0) {
             tc::fence_after_sync();
-            const uint32_t saddr = stage_saddr + (g & 1) * kStageBytes;
-            if (ch.kc == 64) issue_chunk_rt<64>(d_mma, a_mma + ch.a_col, saddr, ch.first ? 0u : 1u);
-            else issue_chunk_rt<48>(d_mma, a_mma + ch.a_col, saddr, ch.first ? 0u : 1u);
-            tc::mma_commit(&bar_free[g & 1]);
-            if (ch.last) tc::mma_commit(&bar_done);
+            for (int c = 0; c < n_chunks; c++, g++) {
+                const SamChunk ch = c_sam_chunks[g % kSamChunks];
+                tc::mbar_wait(&bar_full[g & 1], ph_full[g & 1]);
+                ph_full[g & 1] ^= 1;
+                const uint32_t saddr = stage_saddr + (g & 1) * kStageBytes;
+                if (ch.kc == 64) issue_chunk_rt<64>(d_mma, a_mma + ch.a_col, saddr, ch.first ? 0u : 1u);
+                else issue_chunk_rt<48>(d_mma, a_mma + ch.a_col, saddr, ch.first ? 0u : 1u);
+                tc::mma_commit(&bar_free[g & 1]);
+                if (c == n_chunks - 1) tc::mma_commit(&bar_done);
+                if (g + 1 < total_chunks) {
+                    if (g >= 1) {
+                        tc::mbar_wait(&bar_free[(g + 1) & 1], ph_free[(g + 1) & 1]);
+                        ph_free[(g + 1) & 1] ^= 1;
+                    }
+                    load_chunk(g + 1);
+                }
+            }
         }
         __syncwarp();
-        if (g + 1 < total_chunks) {
-            if (g >= 1) {
-                tc::mbar_wait(&bar_free[(g + 1) & 1], ph_free[(g + 1) & 1]);
-                ph_free[(g + 1) & 1] ^= 1;
-            }
-            load_chunk(g + 1);
-        }
-        g++;
-    };
-    auto wait_layer = [&] {
         tc::mbar_wait(&bar_done, ph_done);
         ph_done ^= 1;
         tc::fence_after_sync();
@@ -397,7 +397,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         tc::tmem_st_wait();
     };
 
-    if (total_chunks) load_chunk(0);
+    if (tid == 0 && total_chunks) load_chunk(0);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- input tile [128,163] fp32 -> shared memory (coalesced 16-byte copies; the buffer is padded to whole tiles) ----
         __syncthreads();   // the previous tile's readers of xt are done
@@ -407,25 +407,18 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
             for (int i = tid; i < 128 * kSamIn / 4; i += kHeadThreads) dst[i] = __ldg(src + i);
         }
         __syncthreads();
-        (void)xt_saddr;
         stage_input();
-        for (int c = 0; c < 3; c++) consume();          // layer 0: 163 -> 256
-        wait_layer();
+        run_chunks(3);          // layer 0: 163 -> 256
         epilogue_to_a(b0);
-        for (int c = 0; c < 4; c++) consume();          // layer 1
-        wait_layer();
+        run_chunks(4);          // layer 1
         epilogue_to_a(b1);
-        for (int c = 0; c < 4; c++) consume();          // layer 2, hidden part  (columns 0..255 of the [256,419] weight)
-        wait_layer();                                   // the MMAs have read A: it can be overwritten with the input again
+        run_chunks(4);          // layer 2, hidden part (columns 0..255 of the [256,419] weight); its MMAs have read A when this returns
         stage_input();
-        for (int c = 0; c < 3; c++) consume();          // layer 2, skip part    (columns 256..418), accumulates onto D
-        wait_layer();
+        run_chunks(3);          // layer 2, skip part (columns 256..418), accumulates onto D
         epilogue_to_a(b2);
-        for (int c = 0; c < 4; c++) consume();          // layer 3
-        wait_layer();
+        run_chunks(4);          // layer 3
         epilogue_to_a(b3);
-        for (int c = 0; c < 4; c++) consume();          // layer 4 (no activation)
-        wait_layer();
+        run_chunks(4);          // layer 4 (no activation)
         // ---- bias + LayerNorm(256, eps 1e-5, affine) + store; one thread per ray (part 0), three passes over its TMEM row ----
         if (part == 0) {
             const uint32_t ray = tile * 128 + row;

@@ -60,6 +60,18 @@ __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// ---- TMA bulk copy (cp.async.bulk, the 1-D form of the tensor memory accelerator; SASS: UBLKCP) ----------------------------
+// One thread arms the mbarrier with the byte count and issues the copy; the barrier completes when the bytes have landed in
+// shared memory (written through the async proxy, which is also the proxy tcgen05.mma reads through: no proxy fence needed).
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(uint32_t dst_saddr, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr), "l"(src),
+                 "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
 // ---- descriptors --------------------------------------------------------------------------------------------
 // Shared-memory operand descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor): core matrix = 8 rows x 16 B
 // stored contiguously (128 B); SBO = byte distance between core matrices adjacent along N, LBO = along K.
