@@ -358,15 +358,18 @@ __device__ __forceinline__ void split_bf16(float v, __nv_bfloat16& hi, __nv_bflo
     hi = __float2bfloat16_rn(v);
     lo = __float2bfloat16_rn(v - __bfloat162float(hi));
 }
-// 16 fp32 values -> 8 columns of bf16 hi pairs + 8 columns of bf16 lo pairs (even k in the low half of the column)
+// 16 fp32 values -> 8 columns of bf16 hi pairs + 8 columns of bf16 lo pairs (even k in the low half of the column).
+// Paired conversions (cvt.rn.bf16x2.f32): 6 instructions per pair of values.
 __device__ __forceinline__ void pack_split16(const float (&v)[16], uint32_t (&hi)[8], uint32_t (&lo)[8]) {
 #pragma unroll
     for (int i = 0; i < 8; i++) {
-        __nv_bfloat16 h0, l0, h1, l1;
-        split_bf16(v[2 * i], h0, l0);
-        split_bf16(v[2 * i + 1], h1, l1);
-        hi[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        lo[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);     // .x (low half) = v[2i]
+        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+        const float r0 = v[2 * i] - __uint_as_float(hb << 16);                       // bf16 -> fp32 is a shift
+        const float r1 = v[2 * i + 1] - __uint_as_float(hb & 0xffff0000u);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(r0, r1);
+        hi[i] = hb;
+        lo[i] = *reinterpret_cast<const uint32_t*>(&l);
     }
 }
 // element index (bf16 units) inside an [N x K] K-major no-swizzle operand image: core matrix = 8 n x 8 k (16 B per row)
