@@ -860,21 +860,38 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             const int nl = (int)p.mgrid.L;
             // row-major [ray,32,K] (reference tensor layout) or tile-transposed [row/128][K][128] for the tensor-core head
             // (heads.cu): there lane <-> consecutive row, so every store below is one coalesced 128-byte line per warp
-            const size_t row = (size_t)ray * 32 + home;
+            const int K = 8 * nl + 15;
             const size_t kstride = p.mask_tiled ? 128 : 1;
-            float* dst = p.mask_tiled ? p.mask_in + (row >> 7) * (size_t)(8 * nl + 15) * 128 + (row & 127) : p.mask_in + row * (8 * nl + 15);
-#pragma unroll 1
-            for (int l = 0; l < nl; l++) {
-                float o[8];
-                if (inside) {
-                    encode_level<8>(p.mgrid, l, x01, o);
-                } else {
+            auto row_ptr = [&](int sample) {
+                const size_t row = (size_t)ray * 32 + sample;
+                return p.mask_tiled ? p.mask_in + (row >> 7) * (size_t)K * 128 + (row & 127) : p.mask_in + row * K;
+            };
+            // m_grid(x) per sample with quarter-row gathers (see quarter_level): lanes (s8, part) = (sample mod 8, channel pair),
+            // four passes of 8 samples; every lane writes its two channels of its pass's sample
+            {
+                const int s8 = lane >> 2, part = lane & 3;
+                float xs[4][3];
+                bool ins[4];
 #pragma unroll
-                    for (int c = 0; c < 8; c++) o[c] = 0.f;
+                for (int ps = 0; ps < 4; ps++) {
+                    const int srcl = 8 * ps + s8;
+#pragma unroll
+                    for (int d = 0; d < 3; d++) xs[ps][d] = __shfl_sync(kFull, x01[d], srcl);
+                    ins[ps] = __shfl_sync(kFull, inside ? 1 : 0, srcl) != 0;
                 }
+#pragma unroll 1
+                for (int l = 0; l < nl; l++) {
 #pragma unroll
-                for (int c = 0; c < 8; c++) dst[(8 * l + c) * kstride] = o[c];
+                    for (int ps = 0; ps < 4; ps++) {
+                        float o0, o1;
+                        quarter_level(p.mgrid, l, xs[ps], part, o0, o1);
+                        float* dst = row_ptr(8 * ps + s8) + (size_t)(8 * l + 2 * part) * kstride;
+                        dst[0] = ins[ps] ? o0 : 0.f;
+                        dst[kstride] = ins[ps] ? o1 : 0.f;
+                    }
+                }
             }
+            float* dst = row_ptr(home);
 #pragma unroll
             for (int c = 0; c < 15; c++) dst[(8 * nl + c) * kstride] = f16[c + 1];
         }
