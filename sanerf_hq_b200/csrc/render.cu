@@ -465,10 +465,14 @@ __device__ __forceinline__ void sample_pdf_warp(const float* w, const float* bin
 #pragma unroll 1
     for (int k = lane; k < TN; k += 32) {
         const float uk = u[k];
-        int lo = 0, hi = T0 + 1;               // searchsorted(cdf, u, right=True): #entries <= u
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (cdf[mid] <= uk) lo = mid + 1; else hi = mid;
+        // searchsorted(cdf, u, right=True) = number of the T0+1 sorted entries that are <= u: branch-free descent over
+        // power-of-two strides (cdf[0] = 0 <= u always; T0 + 1 <= 129 < 256)
+        int lo = 0;
+#pragma unroll
+        for (int step = 128; step >= 1; step >>= 1) {
+            const int probe = lo + step;
+            const bool ok = probe <= T0 + 1 && cdf[min(probe, T0 + 1) - 1] <= uk;
+            lo = ok ? probe : lo;
         }
         const int below = min(max(lo - 1, 0), T0), above = min(lo, T0);
         const float c0 = cdf[below], c1 = cdf[above], g0 = bins[below], g1 = bins[above];
