@@ -165,8 +165,10 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": "Mrays/sec (RGB+feat render, 800x800)", "value": value, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload} {args.height}x{args.width}, hashgrid L=16 T=2^19, MLP 2x64, samples 128+64+32",
-                       "rays_per_step": chunks_per_step * 4096, "device": "host CPU"},
+            "config": {"workload": f"{args.workload} {args.height}x{args.width} per GPU (global frame {args.height}x{args.width}), hashgrid L=16 "
+                                   f"T=2^19, MLP 2x64, samples 128+64+32, reference algorithm in chunks of 4096 rays on the host CPU",
+                       "rays_per_step": chunks_per_step * 4096, "device": "host CPU",
+                       "weights": "random init: seed-0 constructor, hash tables U(-1,1)"},
             "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": cores, "kind": "port",
                              "sample": f"per step: {sample}"},
             "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -289,7 +291,8 @@ def main():
             kern_ms = tot / reps
 
         # ---- end-to-end arm: host rays -> H2D -> render (public API) -> D2H of the image -----------
-        img_host = torch.empty(n_total if world > 1 else n_local, 3).pin_memory()
+        # rank 0 reads the whole (gathered) frame back, like the reference's rank-0 image writer; the other ranks read nothing
+        img_host = torch.empty(n_total, 3).pin_memory() if rank == 0 else None
         o_dev, d_dev = torch.empty(n_local, 3, device=dev), torch.empty(n_local, 3, device=dev)
 
         def step_e2e(i):
@@ -297,7 +300,8 @@ def main():
             o_dev.copy_(ho, non_blocking=True)
             d_dev.copy_(hd, non_blocking=True)
             out = render_frame(o_dev, d_dev)
-            img_host.copy_(out["image"], non_blocking=True)
+            if img_host is not None:
+                img_host.copy_(out["image"], non_blocking=True)
 
         e2e_ms = timed_loop(step_e2e, args.steps, args.warmup)[0] / args.steps
         e2e_value = n_total / (e2e_ms * 1e-3) / 1e6
@@ -334,7 +338,7 @@ def main():
                          "kernel_ms": k_ms, "algorithmic_bytes_per_ray": BYTES_PER_RAY[wl],
                          "mlp_tflops": FLOPS_PER_RAY[wl] * n_local / (k_ms * 1e-3) / 1e12},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * n_local * 12 * world,
-                    "d2h_bytes_per_step": int(img_host.numel() * 4)},
+                    "d2h_bytes_per_step": int(img_host.numel() * 4), "d2h": "rank 0 reads the gathered image"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
