@@ -371,7 +371,8 @@ struct Smem {
     static constexpr int prop_w1 = prop_w0 + 4 * 16 * PKP;   // [2][16]
     // grid_mlp weights as tensor-core operand images (tc.cuh: K-major core matrices), tf32 hi part then lo part
     static constexpr int grid_w0 = (prop_w1 + 2 * 16 + 31) & ~31;  // 2 x [HG][GK]   (128-byte aligned)
-    static constexpr int grid_w1 = grid_w0 + 2 * HG * GK;          // hidden layers: bf16 hi + lo images, 2 x [HG][HG] bf16
+    static constexpr int GKP = (GK + 15) & ~15;                    // first-layer K padded to the bf16 MMA step
+    static constexpr int grid_w1 = grid_w0 + HG * GKP;             // all three layers: bf16 hi + lo images (2 x [N][K] bf16)
     static constexpr int grid_w2 = grid_w1 + HG * HG;              // 2 x [16][HG] bf16
     static constexpr int view_w0 = grid_w2 + 16 * HG;              // [32][VP]  (rows >= Hv zero)
     static constexpr int view_w1 = view_w0 + 32 * VP;        // [32][VP]
@@ -379,12 +380,15 @@ struct Smem {
     static constexpr int utab = view_w2 + 3 * 32;            // u65 (68 slots) + u33 (36 slots)
     static constexpr int scratch = (utab + 68 + 36 + 3) & ~3;
     // per-warp scratch
-    static constexpr int s_bins = 0;      // [2][132]
-    static constexpr int s_ds = 264;      // [128]
-    static constexpr int s_cdf = 392;     // [132]
-    static constexpr int per_warp = 524;
+    // per-warp scratch.  The stage-0 bins are linspace(0,1,129) and never stored; the 33 final-stage bins live in the upper
+    // half of ds (stages 1 and 2 only use ds[0..63]).  Keeping the CTA at <= 63 KB of shared memory selects the 64 KB
+    // carve-out, i.e. 164 KB instead of 128 KB of L1 for the hash-table gathers.
+    static constexpr int s_b65 = 0;       // [68]  bins after the first resampling
+    static constexpr int s_ds = 68;       // [128] delta*sigma / weights; [64..99] = the 33 bins of the final stage
+    static constexpr int s_cdf = 196;     // [132]
+    static constexpr int per_warp = 328;
     static constexpr int total = scratch + kWarps * per_warp;
-    static_assert(GK % 8 == 0 && GK <= 32 && HG % 16 == 0 && HG <= 64, "grid MLP widths (tc::group_layer)");
+    static_assert(GK % 8 == 0 && GK <= 32 && HG % 16 == 0 && HG <= 64, "grid MLP widths (tc::group_layer_from_tmem)");
 };
 
 template <int PL, int GL, int HG, int HV>
@@ -395,7 +399,16 @@ __device__ void stage_weights(float* sm, const RenderParams& p) {
         tc::stage_split_weights<16, S::PK, S::PKP>(sm + S::prop_w0 + e * 2 * 16 * S::PKP, sm + S::prop_w0 + (e * 2 + 1) * 16 * S::PKP,
                                                    p.prop_w0[e], tid, kThreads);
     for (int i = tid; i < 32; i += kThreads) sm[S::prop_w1 + i] = __ldg(p.prop_w1[i / 16] + (i % 16));
-    tc::stage_split_weights<HG, S::GK, S::GK>(sm + S::grid_w0, sm + S::grid_w0 + HG * S::GK, p.grid_w[0], tid, kThreads);
+    {
+        __nv_bfloat16* w0 = reinterpret_cast<__nv_bfloat16*>(sm + S::grid_w0);
+        for (int i = tid; i < HG * S::GKP; i += kThreads) {
+            const int n = i / S::GKP, k = i % S::GKP;
+            __nv_bfloat16 h, l;
+            tc::split_bf16(k < S::GK ? __ldg(p.grid_w[0] + n * S::GK + k) : 0.f, h, l);
+            w0[tc::bf16_img_index(n, k, HG)] = h;
+            w0[HG * S::GKP + tc::bf16_img_index(n, k, HG)] = l;
+        }
+    }
     {
         __nv_bfloat16* w1 = reinterpret_cast<__nv_bfloat16*>(sm + S::grid_w1);
         __nv_bfloat16* w2 = reinterpret_cast<__nv_bfloat16*>(sm + S::grid_w2);
@@ -439,8 +452,10 @@ __device__ __forceinline__ void weights_from_ds(float* ds, int T, int lane, bool
 // sample_pdf (renderer.py:84-119), perturb=False.  w[] = T0 weights, bins[] = T0+1 bins (shared);
 // writes TN new bins; cdf[] is scratch (T0+1).  u = linspace(.5/TN, 1-.5/TN, TN) table (shared).
 // T0 (<= 128) and TN are runtime values so that ONE copy of this code serves both resampling steps.
+// bins == nullptr: the input bins are linspace(0, 1, T0+1) (bin j = j / T0, exact for T0 a power of two).
 __device__ __forceinline__ void sample_pdf_warp(const float* w, const float* bins, float* cdf, const float* u, float* out, int T0, int TN,
                                                 int lane, int16_t* inds_out) {
+    const float inv_t0 = 1.0f / (float)T0;
     const int per = T0 / 32;                   // <= 4
     float wp[4];
     float part = 0.f;
@@ -475,7 +490,8 @@ __device__ __forceinline__ void sample_pdf_warp(const float* w, const float* bin
             lo = ok ? probe : lo;
         }
         const int below = min(max(lo - 1, 0), T0), above = min(lo, T0);
-        const float c0 = cdf[below], c1 = cdf[above], g0 = bins[below], g1 = bins[above];
+        const float c0 = cdf[below], c1 = cdf[above];
+        const float g0 = bins ? bins[below] : (float)below * inv_t0, g1 = bins ? bins[above] : (float)above * inv_t0;
         float t = nan_to_num0(__fdiv_rn(__fsub_rn(uk, c0), __fsub_rn(c1, c0)));
         t = fminf(fmaxf(t, 0.f), 1.f);
         out[k] = __fadd_rn(g0, __fmul_rn(t, __fsub_rn(g1, g0)));
@@ -550,8 +566,9 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, int
     for (int i = 0; i < T / 64; i++) {
         const int ja = lane + 64 * i, jb = ja + 32;
         float tmid, da, db, xa[3], xb[3];
-        const bool ina = sample_point(r, bins[ja], bins[ja + 1], tmid, da, xa);
-        const bool inb = sample_point(r, bins[jb], bins[jb + 1], tmid, db, xb);
+        const float inv_t = 1.0f / (float)T;   // bins == nullptr: linspace(0,1,T+1) (renderer.py:262-266; j/T is exact)
+        const bool ina = sample_point(r, bins ? bins[ja] : (float)ja * inv_t, bins ? bins[ja + 1] : (float)(ja + 1) * inv_t, tmid, da, xa);
+        const bool inb = sample_point(r, bins ? bins[jb] : (float)jb * inv_t, bins ? bins[jb + 1] : (float)(jb + 1) * inv_t, tmid, db, xb);
         float feata[S::PKP], featb[S::PKP];
         {
             float fa[2 * PL], fb[2 * PL];
@@ -610,9 +627,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     auto tmem_end = [&] { if constexpr (kShareSlots) tc::group_release(grp, &tmem_free_mask, my_slot); };
 
     float* scratch = sm + S::scratch + warp * S::per_warp;
-    float* binsA = scratch + S::s_bins;
-    float* binsB = binsA + 132;
+    float* b65 = scratch + S::s_b65;
     float* ds = scratch + S::s_ds;
+    float* b33 = ds + 64;
     float* cdf = scratch + S::s_cdf;
     const float* u65 = sm + S::utab;
     const float* u33 = sm + S::utab + 68;
@@ -659,78 +676,71 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         r.s_near = spacing(near);
         r.s_far = spacing(far);
 
-        // ---- stage 0: uniform bins linspace(0,1,129) (renderer.py:262-266; i/128 is exact) ------
-        for (int j = lane; j <= kMaxT; j += 32) binsA[j] = (float)j * (1.0f / kMaxT);
-        __syncwarp();
-        // one copy of the proposal-stage code serves both stages (runtime network index / sample count): the ray loop is
-        // instruction-fetch sensitive, so its SASS footprint matters
-        {
-            float* bin_in = binsA;
-            float* bin_out = binsB;
+        // ---- stages 0 and 1: proposal networks + resampling.  One copy of the code serves both (runtime network index /
+        // sample count): the ray loop is instruction-fetch sensitive, so its SASS footprint matters.  Stage 0 samples the
+        // uniform bins linspace(0,1,129) (never stored), writes 65 bins; stage 1 reads them and writes the 33 final bins.
 #pragma unroll 1
-            for (int st = 0; st < 2; st++) {
-                const int T = st ? kMaxT / 2 : kMaxT, TN = T / 2 + 1;
-                proposal_stage<PL, GL, HG>(p, st, T, sm, grp, &tmem_free_mask, my_slot, tmem_base, warp & 3, r, bin_in, ds, lane);
-                weights_from_ds(ds, T, lane, last_opaque);
-                __syncwarp();
-                int16_t* tap = st ? p.inds1 : p.inds0;
-                sample_pdf_warp(ds, bin_in, cdf, st ? u33 : u65, bin_out, T, TN, lane, (tap && active) ? tap + TN * (size_t)ray : nullptr);
-                float* t = bin_in; bin_in = bin_out; bin_out = t;
-            }
-        }   // after two swaps the final-stage bins are in binsA again
+        for (int st = 0; st < 2; st++) {
+            const int T = st ? kMaxT / 2 : kMaxT, TN = T / 2 + 1;
+            const float* bin_in = st ? b65 : nullptr;
+            float* bin_out = st ? b33 : b65;
+            proposal_stage<PL, GL, HG>(p, st, T, sm, grp, &tmem_free_mask, my_slot, tmem_base, warp & 3, r, bin_in, ds, lane);
+            weights_from_ds(ds, T, lane, last_opaque);
+            __syncwarp();
+            int16_t* tap = st ? p.inds1 : p.inds0;
+            sample_pdf_warp(ds, bin_in, cdf, st ? u33 : u65, bin_out, T, TN, lane, (tap && active) ? tap + TN * (size_t)ray : nullptr);
+        }
 
         // ---- stage 2: the radiance field, one sample per lane -----------------------------------
         float tmid, delta, x01[3];
         const int home = lane;   // the sample this lane owns in the final stage
-        const bool inside = sample_point(r, binsA[home], binsA[home + 1], tmid, delta, x01);
+        const bool inside = sample_point(r, b33[home], b33[home + 1], tmid, delta, x01);
         float f16[16];  // grid_mlp output: [0] log-density, [1..15] geo_feat
         {
             // grid_mlp 2L -> Hg -> Hg -> 16 (ReLU, no bias; network.py:94) on the tensor core.  The 4 warps of the group put their
             // 4 x 32 samples into the 128 TMEM lanes.  The hash-grid features stream into the A operand as they are gathered
-            // (tf32 hi | lo, 3xTF32 for the first layer); the two hidden layers never leave tensor memory
-            // (tc::group_layer_from_tmem, bf16 hi | lo split operands); only the 16 outputs come back to registers.
-            constexpr int GK = 2 * GL;
-            constexpr int LB = GL % 4 == 0 ? 4 : GL;   // levels per tcgen05.st block (8 columns)
-            static_assert(LB == 4, "grid levels come in blocks of 4");
+            // (bf16 hi | lo split operands, two features per 32-bit column); the two hidden layers never leave tensor memory
+            // (tc::group_layer_from_tmem); only the 16 outputs come back to registers.
+            constexpr int GKP = S::GKP;                  // K of the first layer padded to 16
+            static_assert(GL % 4 == 0, "grid levels come in blocks of 4");
             tmem_begin();
             {
                 LevelLoads buf0, buf1;             // levels 4*lb and 4*lb+1 are in flight at the top of each iteration
                 level_issue(p.grid, 0, x01, buf0);
                 level_issue(p.grid, 1, x01, buf1);
 #pragma unroll 1
-                for (int lb = 0; lb < GL / 4; lb++) {
-                    uint32_t hi[8], lo[8];
+                for (int lb = 0; lb < GKP / 8; lb++) {
+                    // 4 levels = 8 features = 4 packed bf16x2 columns of hi and of lo (a level's two channels share a column)
+                    uint32_t hi[4], lo[4];
 #pragma unroll
                     for (int j = 0; j < 4; j++) {
                         const int l = 4 * lb + j;
-                        float o0, o1;
-                        if (j % 2 == 0) {
-                            level_finish(buf0, o0, o1);
-                            if (l + 2 < GL) level_issue(p.grid, l + 2, x01, buf0);
-                        } else {
-                            level_finish(buf1, o0, o1);
-                            if (l + 2 < GL) level_issue(p.grid, l + 2, x01, buf1);
+                        float o0 = 0.f, o1 = 0.f;
+                        if (l < GL) {                  // uniform; false only in the K padding of the small network
+                            if (j % 2 == 0) {
+                                level_finish(buf0, o0, o1);
+                                if (l + 2 < GL) level_issue(p.grid, l + 2, x01, buf0);
+                            } else {
+                                level_finish(buf1, o0, o1);
+                                if (l + 2 < GL) level_issue(p.grid, l + 2, x01, buf1);
+                            }
                         }
                         o0 = inside ? o0 : 0.f;
                         o1 = inside ? o1 : 0.f;
-                        hi[2 * j] = tc::tf32_hi(o0);
-                        lo[2 * j] = tc::tf32_lo(o0, hi[2 * j]);
-                        hi[2 * j + 1] = tc::tf32_hi(o1);
-                        lo[2 * j + 1] = tc::tf32_lo(o1, hi[2 * j + 1]);
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+                        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+                        const __nv_bfloat162 lw = __floats2bfloat162_rn(o0 - __uint_as_float(hb << 16), o1 - __uint_as_float(hb & 0xffff0000u));
+                        hi[j] = hb;
+                        lo[j] = *reinterpret_cast<const uint32_t*>(&lw);
                     }
-                    tc::tmem_st8(grp.a_rw + 8 * lb, hi);
-                    tc::tmem_st8(grp.a_rw + GK + 8 * lb, lo);
+                    tc::tmem_st4(grp.a_rw + 4 * lb, hi);
+                    tc::tmem_st4(grp.a_rw + GKP / 2 + 4 * lb, lo);
                 }
             }
             {
                 const uint32_t d_mma = grp.d_mma, a_mma = grp.a_mma;
-                const float* w0h = sm + S::grid_w0;
-                const float* w0l = w0h + HG * GK;
-                tc::group_round(grp, [&] {
-                    tc::issue_layer<HG, GK / 8>(d_mma, a_mma, w0h, 0u);
-                    tc::issue_layer<HG, GK / 8>(d_mma, a_mma, w0l, 1u);
-                    tc::issue_layer<HG, GK / 8>(d_mma, a_mma + GK, w0h, 1u);
-                });
+                const __nv_bfloat16* w0 = reinterpret_cast<const __nv_bfloat16*>(sm + S::grid_w0);
+                tc::group_round(grp, [&] { tc::issue_layer_bf16<HG, GKP>(d_mma, a_mma, w0, w0 + HG * GKP); });
             }
             const __nv_bfloat16* w1 = reinterpret_cast<const __nv_bfloat16*>(sm + S::grid_w1);
             const __nv_bfloat16* w2 = reinterpret_cast<const __nv_bfloat16*>(sm + S::grid_w2);
@@ -804,8 +814,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         if (p.weights2 && active) p.weights2[32 * (size_t)ray + home] = w;
         if (p.sigma2 && active) p.sigma2[32 * (size_t)ray + home] = sigma;
         if (p.bins2 && active) {
-            p.bins2[33 * (size_t)ray + lane] = binsA[lane];
-            if (lane == 0) p.bins2[33 * (size_t)ray + 32] = binsA[32];
+            p.bins2[33 * (size_t)ray + lane] = b33[lane];
+            if (lane == 0) p.bins2[33 * (size_t)ray + 32] = b33[32];
         }
         if (p.f_image && active && lane < 31) {
             float v = fimg[0];
@@ -973,6 +983,7 @@ static int launch_render(const RenderParams& p, bool sam, bool mask, cudaStream_
             cudaGetLastError();                                                                                 \
             return SANERF_E_SMEM;                                                                               \
         }                                                                                                       \
+        cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 2048) * 100 / (228 * 1024)) + 1); \
         kfn<<<blocks, kThreads, smem, st>>>(p);                                                                 \
     } while (0)
     if (sam && mask) SANERF_LAUNCH(true, true);
