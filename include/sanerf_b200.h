@@ -185,6 +185,14 @@ typedef struct {
     float *sigma2;                  /* [N,32]  final-stage sigma */
     float *bins2;                   /* [N,33]  final-stage bins (normalised) */
     float *f_image;                 /* [N,31]  composited deferred-shading feature */
+    /* optional in-kernel ray generation (replaces the full-image branch of nerf/utils.py::get_rays :262-287):
+     * when cam_w > 0, rays_o / rays_d may be NULL and ray n is the pixel with linear index q = cam_ray0 + n (col = q % cam_w,
+     * row = q / cam_w) of a pinhole camera: dirs = ((col+.5-cx)/fx, -(row+.5-cy)/fy, -1), rays_d = R dirs (unnormalised), rays_o = t. */
+    uint32_t cam_w, cam_ray0;
+    float cam_intrinsics[4];        /* fx, fy, cx, cy */
+    float cam_pose[12];             /* rows 0..2 of the 4x4 cam2world matrix, row-major: [R | t] */
+    /* optional 8-bit image (trainer.py:1140-1143 `(pred * 255).astype(np.uint8)`): [N,3] uint8 */
+    uint8_t *image_u8;
 } sanerf_render_args_t;
 
 /* `model` and `args` are HOST structs (copied at launch); the pointers inside are device pointers.

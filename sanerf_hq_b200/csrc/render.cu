@@ -86,6 +86,10 @@ struct RenderParams {
     float* sigma2;
     float* bins2;
     float* f_image;
+    uint32_t cam_w, cam_ray0;
+    float cam_intr[4];
+    float cam_pose[12];
+    uint8_t* image_u8;
 };
 
 // ---- small helpers ------------------------------------------------------------------------------
@@ -645,8 +649,21 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         const uint32_t ray = active ? base + warp : p.N - 1;
         // ---- ray setup: near/far from the AABB (renderer.py:122-139, 231-235) -------------------
         RayCtx r;
-        r.ox = __ldg(p.rays_o + 3 * (size_t)ray); r.oy = __ldg(p.rays_o + 3 * (size_t)ray + 1); r.oz = __ldg(p.rays_o + 3 * (size_t)ray + 2);
-        r.dx = __ldg(p.rays_d + 3 * (size_t)ray); r.dy = __ldg(p.rays_d + 3 * (size_t)ray + 1); r.dz = __ldg(p.rays_d + 3 * (size_t)ray + 2);
+        if (p.cam_w) {
+            // pinhole ray of pixel (col, row) (nerf/utils.py:262-277): pixel centres at +0.5, y and z flipped, rays_d = R dirs
+            // left unnormalised (metric depth), rays_o = t
+            const uint32_t q = p.cam_ray0 + ray, col = q % p.cam_w, rowi = q / p.cam_w;
+            const float xs = __fdiv_rn(__fsub_rn((float)col + 0.5f, p.cam_intr[2]), p.cam_intr[0]);
+            const float ys = -__fdiv_rn(__fsub_rn((float)rowi + 0.5f, p.cam_intr[3]), p.cam_intr[1]);
+            const float zs = -1.0f;
+            r.dx = __fmaf_rn(zs, p.cam_pose[2], __fmaf_rn(ys, p.cam_pose[1], __fmul_rn(xs, p.cam_pose[0])));
+            r.dy = __fmaf_rn(zs, p.cam_pose[6], __fmaf_rn(ys, p.cam_pose[5], __fmul_rn(xs, p.cam_pose[4])));
+            r.dz = __fmaf_rn(zs, p.cam_pose[10], __fmaf_rn(ys, p.cam_pose[9], __fmul_rn(xs, p.cam_pose[8])));
+            r.ox = p.cam_pose[3]; r.oy = p.cam_pose[7]; r.oz = p.cam_pose[11];
+        } else {
+            r.ox = __ldg(p.rays_o + 3 * (size_t)ray); r.oy = __ldg(p.rays_o + 3 * (size_t)ray + 1); r.oz = __ldg(p.rays_o + 3 * (size_t)ray + 2);
+            r.dx = __ldg(p.rays_d + 3 * (size_t)ray); r.dy = __ldg(p.rays_d + 3 * (size_t)ray + 1); r.dz = __ldg(p.rays_d + 3 * (size_t)ray + 2);
+        }
         r.bound = p.bound;
         {
             const float den = 2.0f * p.bound;
@@ -808,6 +825,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             if (lane < 3) p.image[3 * (size_t)ray + lane] = lane == 0 ? rgb[0] : (lane == 1 ? rgb[1] : rgb[2]);
             if (lane == 3) p.depth[ray] = depth;
             if (lane == 4) p.wsum[ray] = wsum;
+            if (p.image_u8 && lane < 3) {   // numpy's float -> uint8 cast of (pred * 255): truncation toward zero
+                const float v = __fmul_rn(lane == 0 ? rgb[0] : (lane == 1 ? rgb[1] : rgb[2]), 255.0f);
+                p.image_u8[3 * (size_t)ray + lane] = (uint8_t)(int)fminf(fmaxf(v, 0.f), 255.f);
+            }
         }
 
         // ---- parity taps ------------------------------------------------------------------------
@@ -1003,7 +1024,8 @@ extern "C" {
 int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf_stream_t stream) {
     if (!m || !a) return SANERF_E_NULL;
     if (a->N == 0) return 0;
-    if (!a->rays_o || !a->rays_d || !a->image || !a->depth || !a->weights_sum || !m->u65 || !m->u33) return SANERF_E_NULL;
+    if (!a->image || !a->depth || !a->weights_sum || !m->u65 || !m->u33) return SANERF_E_NULL;
+    if (!a->cam_w && (!a->rays_o || !a->rays_d)) return SANERF_E_NULL;
     RenderParams p;
     int rc;
     if ((rc = fill_grid(p.prop[0], m->prop_grid[0], 2))) return rc;
@@ -1034,6 +1056,9 @@ int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf
     p.bg = a->bg_color; p.bg_rows = a->bg_rows; p.bg_scalar = a->bg_scalar;
     p.image = a->image; p.depth = a->depth; p.wsum = a->weights_sum;
     p.sam_in = a->sam_in; p.mask_in = a->mask_in; p.mask_tiled = a->mask_in_tiled;
+    p.cam_w = a->cam_w; p.cam_ray0 = a->cam_ray0; p.image_u8 = a->image_u8;
+    for (int i = 0; i < 4; i++) p.cam_intr[i] = a->cam_intrinsics[i];
+    for (int i = 0; i < 12; i++) p.cam_pose[i] = a->cam_pose[i];
     p.inds0 = a->inds0; p.inds1 = a->inds1; p.weights2 = a->weights2; p.sigma2 = a->sigma2; p.bins2 = a->bins2; p.f_image = a->f_image;
 
     const uint32_t PL = m->prop_grid[0].num_levels, GL = m->grid.num_levels;

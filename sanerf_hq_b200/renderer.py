@@ -184,6 +184,29 @@ class NeRFRenderer(nn.Module):
                     results[k] = v
         return results
 
+    @torch.no_grad()
+    def render_image(self, pose, intrinsics, H, W, rows=None, return_uint8=False, **kwargs):
+        """Render image rows [rows[0], rows[1]) (default: the whole H x W frame) of a pinhole camera WITHOUT materialising rays:
+        the fused kernel derives every ray from `pose` (cam2world [4,4] or [3,4]) and `intrinsics` (fx, fy, cx, cy) exactly
+        like the full-image branch of the reference's nerf/utils.py::get_rays (:262-287).  Same kwargs / result dict as
+        `render`; `return_uint8=True` adds `image_u8` [N,3] = (image * 255) cast like trainer.py:1140-1143.
+        Eval / perturb=False only (the fused path); the model's device is used."""
+        device = next(self.parameters()).device
+        if device.type != "cuda":
+            raise RuntimeError("NeRFRenderer.render_image: the model must be on a CUDA device (there is no CPU path)")
+        kw = dict(kwargs)
+        kw.setdefault("perturb", False)
+        if not self._can_fuse(torch.empty(0, device=device), kw):
+            raise RuntimeError("NeRFRenderer.render_image needs the fused path (eval / no-grad, perturb=False, default sample counts)")
+        r0, r1 = (0, H) if rows is None else rows
+        pose = torch.as_tensor(pose, dtype=torch.float32).reshape(-1, 4)[:3].cpu()
+        camera = (pose.reshape(-1).tolist(), [float(v) for v in intrinsics], int(W), int(r0) * int(W), (int(r1) - int(r0)) * int(W), device)
+        kw.pop("staged", None)
+        if kw.get("return_feats", 0):
+            kw.setdefault("H", r1 - r0)
+            kw.setdefault("W", W)
+        return self._run_fused(None, None, camera=camera, return_uint8=return_uint8, **kw)
+
     def run(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
             return_feats=0, return_mask=0, H=None, W=None, **kwargs):
         if self.opt.render_mesh:
@@ -267,11 +290,14 @@ class NeRFRenderer(nn.Module):
 
     @torch.no_grad()
     def _run_fused(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
-                   return_feats=0, return_mask=0, H=None, W=None, taps=None, **kwargs):
-        rays_o = rays_o.contiguous().float()
-        rays_d = rays_d.contiguous().float()
-        _lib.require_cuda(rays_o, rays_d, what="NeRFRenderer.run")
-        N, device = rays_o.shape[0], rays_o.device
+                   return_feats=0, return_mask=0, H=None, W=None, taps=None, camera=None, return_uint8=False, **kwargs):
+        if camera is None:
+            rays_o = rays_o.contiguous().float()
+            rays_d = rays_d.contiguous().float()
+            _lib.require_cuda(rays_o, rays_d, what="NeRFRenderer.run")
+            N, device = rays_o.shape[0], rays_o.device
+        else:   # rays are generated inside the kernel: camera = (pose 3x4 as 12 floats, (fx, fy, cx, cy), width, first linear pixel index, n_rays, device)
+            N, device = camera[4], camera[5]
         lib = _lib.load()
         for q in self.parameters():
             if q.device != device:
@@ -285,7 +311,19 @@ class NeRFRenderer(nn.Module):
         results = {"weights_sum": weights_sum, "depth": depth, "image": image}
 
         a = _lib.RenderArgsT()
-        a.rays_o, a.rays_d, a.N = rays_o.data_ptr(), rays_d.data_ptr(), N
+        a.N = N
+        if camera is None:
+            a.rays_o, a.rays_d = rays_o.data_ptr(), rays_d.data_ptr()
+        else:
+            a.cam_w, a.cam_ray0 = int(camera[2]), int(camera[3])
+            for i, v in enumerate(camera[1]):
+                a.cam_intrinsics[i] = float(v)
+            for i, v in enumerate(camera[0]):
+                a.cam_pose[i] = float(v)
+        if return_uint8:
+            image_u8 = torch.empty(N, 3, device=device, dtype=torch.uint8)
+            results["image_u8"] = image_u8
+            a.image_u8 = image_u8.data_ptr()
         if cam_near_far is not None:
             cnf = cam_near_far.to(device=device, dtype=torch.float32).contiguous()
             keep.append(cnf)
@@ -342,9 +380,10 @@ class NeRFRenderer(nn.Module):
             a.mask_in_tiled = 1
         sam_full = self._alloc_rows_padded(N, self.samvit_mlp[0].dim_in, device) if want_sam else None
         base = {f: getattr(a, f) for f in ("rays_o", "rays_d", "image", "depth", "weights_sum", "cam_near_far", "bg_color",
-                                           "inds0", "inds1", "weights2", "sigma2", "bins2", "f_image")}
+                                           "inds0", "inds1", "weights2", "sigma2", "bins2", "f_image", "image_u8")}
         strides = {"rays_o": 12, "rays_d": 12, "image": 12, "depth": 4, "weights_sum": 4, "inds0": 130, "inds1": 66,
-                   "weights2": 128, "sigma2": 128, "bins2": 132, "f_image": 124}
+                   "weights2": 128, "sigma2": 128, "bins2": 132, "f_image": 124, "image_u8": 3}
+        cam_ray0 = a.cam_ray0
         user_w2 = base["weights2"]
         for head in range(0, N, chunk):
             n = min(chunk, N - head)
@@ -356,6 +395,7 @@ class NeRFRenderer(nn.Module):
             if base["bg_color"] and a.bg_rows > 1:
                 a.bg_color = base["bg_color"] + head * 12
             a.N = n
+            a.cam_ray0 = cam_ray0 + head
             a.mask_in = mask_in.data_ptr()
             if not user_w2:
                 a.weights2 = w2.data_ptr()

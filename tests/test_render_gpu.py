@@ -183,3 +183,38 @@ def test_training_mode_composed_path_backward():
     for n, p in model.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), n
     assert model.grid.embeddings.grad.abs().sum() > 0 and model.prop_encoders[0].embeddings.grad.abs().sum() > 0
+
+
+@pytest.mark.parametrize("mode", ["rgb", "mask"])
+def test_render_image_generates_the_rays_in_kernel(mode):
+    """`render_image(pose, intrinsics, H, W)` derives the rays inside the fused kernel (reference
+    nerf/utils.py::get_rays, full-image branch) and can emit the 8-bit image of trainer.py:1140-1143.  Must agree with
+    rendering explicitly generated rays: the ray arithmetic is the same up to the matmul's summation order (<= 1 ulp on the
+    directions, which the ill-conditioned far-field spacing amplifies to ~2e-4 on the logits), so outputs agree well inside
+    the 1e-3 path tolerance; the uint8 image is the exact cast of the float image."""
+    from sanerf_hq_b200.rays import get_rays, lego_intrinsics, orbit_pose
+    opt, params, specs = make_case(with_mask=mode == "mask")
+    model = build_model(opt, params)
+    H, W = 40, 64
+    pose, intr = orbit_pose(7), lego_intrinsics(H, W)
+    kw = dict(return_mask=1) if mode == "mask" else {}
+    for rows in (None, (8, 24)):
+        r0, r1 = rows or (0, H)
+        rays_o, rays_d = get_rays(pose, intr, H, W, rows=(r0, r1))
+        want = _render(model, rays_o, rays_d, True, True, **kw)
+        got = model.render_image(pose, intr, H, W, rows=rows, return_uint8=True, **kw)
+        assert set(want) | {"image_u8"} == set(got)
+        for k in want:
+            assert got[k].shape == want[k].shape
+            assert_close(got[k], want[k], 5e-4, f"{mode}/{k}")
+        assert got["image_u8"].dtype == torch.uint8 and tuple(got["image_u8"].shape) == ((r1 - r0) * W, 3)
+        assert torch.equal(got["image_u8"], (got["image"] * 255).clamp(0, 255).to(torch.uint8))
+    # in-kernel rays == reference get_rays formula evaluated in float64 (pixel centres, flipped y/z, unnormalised)
+    rays_o, rays_d = get_rays(pose, intr, H, W)
+    j, i = torch.meshgrid(torch.arange(H, dtype=torch.float64) + 0.5, torch.arange(W, dtype=torch.float64) + 0.5, indexing="ij")
+    fx, fy, cx, cy = intr
+    dirs = torch.stack(((i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)), -1).reshape(-1, 3)
+    want_d = dirs @ pose[:3, :3].double().t()
+    assert (rays_d.double() - want_d).abs().max() < 1e-6
+    with pytest.raises(RuntimeError):
+        model.render_image(pose, intr, H, W, perturb=True)
