@@ -37,6 +37,7 @@ import torch  # noqa: E402
 BYTES_PER_RAY = {"rgb": 94252, "sam": 226348, "mask": 225332}
 FLOPS_PER_RAY = {"rgb": 530560, "sam": 1221760, "mask": 7100544}
 H_FRAME, W_FRAME, N_POSES = 800, 800, 24
+TILE_HINT = os.environ.get("SANERF_BENCH_TILE_HINT", "1") != "0"   # pass image_width= (row-major frame) to the renderer
 
 
 def parse():
@@ -219,10 +220,10 @@ def main():
             # staged + return_feats is impossible in the reference API (`samvit.view(H, W, -1)` on a chunk),
             # so the feature frame is ONE non-staged call over all H*W rays with H, W of this rank's block -- the reference's own
             # call shape (trainer.py:536-537), which it can only afford at 64x64 because it materialises [N,32,128] tensors
-            out = model.render(ro, rd, staged=False, perturb=False, return_feats=1, H=H, W=W)
+            out = model.render(ro, rd, staged=False, perturb=False, return_feats=1, H=H, W=W, image_width=TILE_HINT and W)
             out = {k: (out[k].reshape(-1, out[k].shape[-1]) if k == "samvit" else out[k]) for k in keys}
         else:
-            out = model.render(ro, rd, staged=True, perturb=False, **kw)
+            out = model.render(ro, rd, staged=True, perturb=False, image_width=TILE_HINT and W, **kw)
         if world > 1:
             out = {k: gather_rows(out[k], [n_local] * world) for k in keys}
         return out

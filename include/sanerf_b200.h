@@ -191,6 +191,10 @@ typedef struct {
     uint32_t cam_w, cam_ray0;
     float cam_intrinsics[4];        /* fx, fy, cx, cy */
     float cam_pose[12];             /* rows 0..2 of the 4x4 cam2world matrix, row-major: [R | t] */
+    /* optional traversal hint: the N rays are a row-major image (block) of width tile_w (N % (4*tile_w) == 0, tile_w % 4 == 0):
+     * the kernel then walks 4x4-pixel tiles instead of 16-pixel row segments (better cache reuse between neighbouring rays).
+     * Results are identical; 0 = no assumption. */
+    uint32_t tile_w;
     /* optional 8-bit image (trainer.py:1140-1143 `(pred * 255).astype(np.uint8)`): [N,3] uint8 */
     uint8_t *image_u8;
 } sanerf_render_args_t;

@@ -34,7 +34,7 @@ class RenderArgsT(ctypes.Structure):
                 ("bg_color", _vp), ("bg_rows", _u32), ("bg_scalar", _f32),
                 ("image", _vp), ("depth", _vp), ("weights_sum", _vp), ("sam_in", _vp), ("mask_in", _vp),
                 ("mask_in_tiled", _u32), ("inds0", _vp), ("inds1", _vp), ("weights2", _vp), ("sigma2", _vp), ("bins2", _vp), ("f_image", _vp),
-                ("cam_w", _u32), ("cam_ray0", _u32), ("cam_intrinsics", _f32 * 4), ("cam_pose", _f32 * 12), ("image_u8", _vp)]
+                ("cam_w", _u32), ("cam_ray0", _u32), ("cam_intrinsics", _f32 * 4), ("cam_pose", _f32 * 12), ("tile_w", _u32), ("image_u8", _vp)]
 
 
 # name -> argtypes (restype is int for all but the two noted)

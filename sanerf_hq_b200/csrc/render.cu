@@ -89,6 +89,7 @@ struct RenderParams {
     uint32_t cam_w, cam_ray0;
     float cam_intr[4];
     float cam_pose[12];
+    uint32_t tile_w;
     uint8_t* image_u8;
 };
 
@@ -645,8 +646,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     // whole GPU works on the same ~3 image rows, which keeps the cells they share hot in L2 (measured: giving each CTA one
     // contiguous block of rays instead costs +2 % on the RGB frame and +35 % on the SAM frame, whose 160 MiB table overflows L2)
     for (uint32_t base = blockIdx.x * kWarps; base < p.N; base += total_warps) {
-        const bool active = base + warp < p.N;
-        const uint32_t ray = active ? base + warp : p.N - 1;
+        bool active = base + warp < p.N;
+        uint32_t ray = active ? base + warp : p.N - 1;
+        if (p.tile_w) {   // the 16 warps take a 4x4-pixel tile of the row-major image instead of a 16-pixel row segment
+            const uint32_t tiles_x = p.tile_w >> 2, t = base / kWarps;
+            ray = (4 * (t / tiles_x) + (warp >> 2)) * p.tile_w + 4 * (t % tiles_x) + (warp & 3);
+            active = true;
+        }
         // ---- ray setup: near/far from the AABB (renderer.py:122-139, 231-235) -------------------
         RayCtx r;
         if (p.cam_w) {
@@ -1057,6 +1063,7 @@ int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf
     p.image = a->image; p.depth = a->depth; p.wsum = a->weights_sum;
     p.sam_in = a->sam_in; p.mask_in = a->mask_in; p.mask_tiled = a->mask_in_tiled;
     p.cam_w = a->cam_w; p.cam_ray0 = a->cam_ray0; p.image_u8 = a->image_u8;
+    p.tile_w = (kWarps == 16 && a->tile_w && a->tile_w % 4 == 0 && a->N % (4 * a->tile_w) == 0) ? a->tile_w : 0;
     for (int i = 0; i < 4; i++) p.cam_intr[i] = a->cam_intrinsics[i];
     for (int i = 0; i < 12; i++) p.cam_pose[i] = a->cam_pose[i];
     p.inds0 = a->inds0; p.inds1 = a->inds1; p.weights2 = a->weights2; p.sigma2 = a->sigma2; p.bins2 = a->bins2; p.f_image = a->f_image;
