@@ -34,8 +34,11 @@ namespace sanerf {
 #endif
 constexpr int kWarps = SANERF_RENDER_WARPS;   // warps (= rays in flight) per CTA; 4 warps = one tensor-core group
 constexpr int kGroups = kWarps / 4;
+#ifndef SANERF_PROP_DEPTH
+#define SANERF_PROP_DEPTH 1   // levels of loads in flight per chunk in the proposal gathers (1: 11.90 ms, 2: 11.99 ms)
+#endif
 constexpr bool kShareSlots = kGroups > 4;     // more groups than 128-column TMEM slots: time-share them (tc::group_acquire).
-// Measured on B200 (800x800 RGB frame): 16 warps / 128 registers 12.81 ms; 20 warps / 96 registers 12.82 ms; 24 warps / 80
+// Measured on B200 (800x800 RGB frame): 12 warps 13.9 ms; 16 warps / 128 registers 12.81 ms; 20 warps / 96 registers 12.82 ms; 24 warps / 80
 // registers 13.1 ms -- more resident warps lower the L1 hit rate (90 % -> 83 %) as fast as they hide latency, so the default
 // stays at 16 (no slot sharing, no spills).
 constexpr int kThreads = kWarps * 32;
@@ -577,7 +580,7 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, int
         float feata[S::PKP], featb[S::PKP];
         {
             float fa[2 * PL], fb[2 * PL];
-            gather_levels_x2<PL, (kWarps > 16 ? 1 : 2)>(g, xa, xb, ina, inb, fa, fb);
+            gather_levels_x2<PL, SANERF_PROP_DEPTH>(g, xa, xb, ina, inb, fa, fb);
 #pragma unroll
             for (int k = 0; k < S::PKP; k++) {
                 feata[k] = k < 2 * PL ? fa[k] : 0.f;
