@@ -9,7 +9,8 @@
 //   * activations live in TMEM as the A operand (bf16 hi | bf16 lo, two K values per 32-bit column), one row per TMEM lane;
 //     warps w and w+4 share the 32 lanes of sub-partition w and split the columns between them;
 //   * weights are pre-split into bf16 hi / lo operand images (K-major, no swizzle) by a prepare kernel and streamed from L2
-//     through a double-buffered cp.async ring of K-chunks (the whole MLP is 410 KB of operands -- it does not fit in smem);
+//     through a double-buffered ring of K-chunks filled by TMA bulk copies (cp.async.bulk + mbarrier expect_tx; the whole
+//     MLP is 410 KB of operands -- it does not fit in shared memory); the MMA-issuing thread drives the ring;
 //   * D[128,256] fp32 accumulates in TMEM columns [256,512); the epilogue of a layer reads D, applies leaky_relu, splits to
 //     bf16 hi/lo and writes the next layer's A operand straight back to TMEM columns [0,256);
 //   * split precision: D = Ah*Wh + Ah*Wl + Al*Wh (the dropped Al*Wl is 2^-18 relative), fp32 accumulation;
@@ -83,12 +84,6 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_col, uin
         mma_bf16_ts(d_tmem, a_col + kColsAlo + 8 * j, bh, idesc, 1u);
     }
 }
-
-__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 __global__ void __launch_bounds__(kHeadThreads, 1)
     mask_mlp_kernel(const float* __restrict__ mask_in, const float* __restrict__ weights, const __nv_bfloat16* __restrict__ img,

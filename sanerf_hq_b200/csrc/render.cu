@@ -4,24 +4,25 @@
 // `NeRFRenderer.run` (nerf/renderer.py:221-385, eval mode, perturb=False) for ALL rays of a frame
 // (the reference additionally loops over max_ray_batch chunks, renderer.py:195-217).
 //
-// Mapping: one warp per ray, lanes = samples.  The three sampling stages (128 / 64 / 32 samples,
-// main.py:84-85) run back to back inside the warp:
-//   stage 0,1  positions from the current bins -> L-inf contraction -> proposal hash grid
-//              (L<=5 levels, C=2) -> 2L->16->1 MLP -> sigma -> weights (warp scan) -> sample_pdf
-//              (warp scan for the cdf, per-lane binary search in shared memory)
-//   stage 2    hash grid (L<=16, C=2) -> 2L->Hg->Hg->16 MLP -> sigma, geo_feat -> weights ->
-//              alpha compositing by warp reductions -> deferred view MLP (31->Hv->Hv->3, one
-//              hidden unit per lane) -> sigmoid + background.
-// Optional heads gather the C=8 feature grid (s_grid / m_grid) per sample in the same pass.
-// Nothing per-sample ever goes to HBM except the optional parity taps.
+// Mapping: one warp per ray, lanes = samples; 4 warps form a tensor-core group (128 samples = the 128 TMEM lanes, one
+// MMA row per thread, tc.cuh).  The three sampling stages (128 / 64 / 32 samples, main.py:84-85) run back to back:
+//   stage 0,1  positions from the current bins -> L-inf contraction -> proposal hash grid (L<=5 levels, C=2, software-
+//              pipelined gathers) -> 2L->16 on the tensor core (3xTF32, A and D in TMEM), 16->1 + exp on CUDA cores ->
+//              weights (warp scan) -> sample_pdf (warp scan for the cdf, branch-free per-lane search in shared memory)
+//   stage 2    hash grid (L<=16, C=2) features stream into TMEM as they are gathered -> 2L->Hg->Hg->16 on the tensor core
+//              with the hidden activations resident in TMEM (bf16 hi/lo split operands) -> sigma, geo_feat -> weights ->
+//              alpha compositing by warp reductions -> deferred view MLP (31->Hv->Hv->3, one hidden unit per lane) ->
+//              sigmoid + background.
+// Optional heads gather the C=8 feature grid (s_grid / m_grid) in the same pass with quarter-row loads; their MLPs are the
+// tensor-core kernels of heads.cu.  Nothing per-sample goes to HBM on the RGB path (except the optional parity taps).
 //
-// Shared memory: all MLP weights staged once per CTA (persistent CTAs, one per SM) + 2 KB of
-// per-warp scratch (bins ping-pong, delta*sigma / weights, cdf).  Hash tables are read through
-// L1/L2 (54 MiB of RGB tables are L2-resident on B200's 126 MB L2).
+// Shared memory (63 KB -> the 64 KB carve-out leaves 164 KB of L1 to the gathers): tensor-core operand images of all MLP
+// weights, staged once per persistent CTA (one per SM), + 1.3 KB of per-warp scratch (bins, delta*sigma / weights, cdf).
+// Hash tables are read through L1/L2 (the 54 MiB of RGB tables are L2-resident on B200's 126 MB L2).
 //
-// Arithmetic follows the reference op by op (unfused mul/add where torch rounds twice, IEEE
-// division, expf), see the comments citing renderer.py lines; reductions use a different
-// association than ATen's (warp tree), which is within fp32 summation-order noise.
+// Arithmetic follows the reference op by op outside the MLPs (unfused mul/add where torch rounds twice, correctly rounded
+// reciprocals, expf), see the comments citing renderer.py lines; reductions use a different association than ATen's (warp
+// tree), which is within fp32 summation-order noise; the MLPs use split-precision tensor-core math.
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -152,74 +153,9 @@ __device__ __forceinline__ void floor_split(float pos, uint32_t& cell, float& fr
     frac = pos - (t - 8388608.0f);
 }
 
-// One level of a C-channel grid at a point in [0,1]^3: same arithmetic as grid_encode.cu / the
-// reference kernel (gridencoder.cu:140-195) with the per-level constants taken from GridDev.
-template <int C>
-__device__ __forceinline__ void encode_level(const GridDev& g, int l, const float (&x)[3], float (&out)[C]) {
-    const uint32_t res = g.res[l];
-    const uint32_t hmask = g.hmask[l];
-    const float* __restrict__ rows = g.emb + (size_t)g.off[l] * C;
-    const float resf = (float)res, top = (float)(res - 1);
-    uint32_t b0[3], b1[3];
-    float f[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        float pos = fminf(fmaxf(__fmaf_rn(x[d], resf, -0.5f), 0.0f), top);
-        floor_split(pos, b0[d], f[d]);
-        b1[d] = min(b0[d] + 1, res - 1);
-    }
-    uint32_t row[8];
-    float w[8];
-    if (hmask == 0) {  // dense level: x + y*res + z*res^2 < rows, no modulo needed
-        const uint32_t y0 = b0[1] * res, y1 = b1[1] * res, z0 = b0[2] * res * res, z1 = b1[2] * res * res;
-#pragma unroll
-        for (int i = 0; i < 8; i++) row[i] = ((i & 1) ? b1[0] : b0[0]) + ((i & 2) ? y1 : y0) + ((i & 4) ? z1 : z0);
-    } else {
-        const uint32_t y0 = b0[1] * 2654435761u, y1 = b1[1] * 2654435761u, z0 = b0[2] * 805459861u, z1 = b1[2] * 805459861u;
-#pragma unroll
-        for (int i = 0; i < 8; i++) row[i] = (((i & 1) ? b1[0] : b0[0]) ^ ((i & 2) ? y1 : y0) ^ ((i & 4) ? z1 : z0)) & hmask;
-    }
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        float ww = (i & 1) ? f[0] : 1 - f[0];
-        ww *= (i & 2) ? f[1] : 1 - f[1];
-        ww *= (i & 4) ? f[2] : 1 - f[2];
-        w[i] = ww;
-    }
-    if constexpr (C == 2) {
-        float2 v[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = __ldg(reinterpret_cast<const float2*>(rows) + row[i]);
-        out[0] = 0.f; out[1] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            out[0] = __fmaf_rn(w[i], v[i].x, out[0]);
-            out[1] = __fmaf_rn(w[i], v[i].y, out[1]);
-        }
-    } else {
-        static_assert(C == 8, "feature grids use 8 channels");
-        float4 va[8], vb[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const float4* p = reinterpret_cast<const float4*>(rows) + (size_t)row[i] * 2;
-            va[i] = __ldg(p);
-            vb[i] = __ldg(p + 1);
-        }
-#pragma unroll
-        for (int c = 0; c < 8; c++) out[c] = 0.f;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            out[0] = __fmaf_rn(w[i], va[i].x, out[0]); out[1] = __fmaf_rn(w[i], va[i].y, out[1]);
-            out[2] = __fmaf_rn(w[i], va[i].z, out[2]); out[3] = __fmaf_rn(w[i], va[i].w, out[3]);
-            out[4] = __fmaf_rn(w[i], vb[i].x, out[4]); out[5] = __fmaf_rn(w[i], vb[i].y, out[5]);
-            out[6] = __fmaf_rn(w[i], vb[i].z, out[6]); out[7] = __fmaf_rn(w[i], vb[i].w, out[7]);
-        }
-    }
-}
-
 // ---- software-pipelined C=2 gathers ------------------------------------------------------------------------------------
 // A level is split into `issue` (cell lookup + the 8 row loads) and `finish` (trilinear blend, same FMA order as
-// encode_level / the reference kernel); gather_levels keeps DEPTH levels of loads in flight per thread so the L1/L2
+// the reference kernel, gridencoder.cu:170-195); the callers keep one or two levels of loads in flight per thread so the L1/L2
 // latency of one level hides behind the index arithmetic and the loads of the next ones.
 struct LevelLoads {
     float2 v[8];
@@ -266,22 +202,6 @@ __device__ __forceinline__ void level_finish(const LevelLoads& o, float& o0, flo
     o1 = a1;
 }
 
-// feat[2l], feat[2l+1] = level l of grid g at x (in [0,1]^3); zeros when the point is outside (gridencoder.cu:105-130)
-template <int L, int DEPTH>
-__device__ __forceinline__ void gather_levels(const GridDev& g, const float (&x)[3], bool inside, float (&feat)[2 * L]) {
-    LevelLoads buf[DEPTH];
-#pragma unroll
-    for (int d = 0; d < DEPTH && d < L; d++) level_issue(g, d, x, buf[d]);
-#pragma unroll
-    for (int l = 0; l < L; l++) {
-        float o0, o1;
-        level_finish(buf[l % DEPTH], o0, o1);
-        if (l + DEPTH < L) level_issue(g, l + DEPTH, x, buf[l % DEPTH]);
-        feat[2 * l] = inside ? o0 : 0.f;
-        feat[2 * l + 1] = inside ? o1 : 0.f;
-    }
-}
-
 // two points at once (two sample chunks of the same ray): twice the independent loads in flight per thread
 template <int L, int DEPTH>
 __device__ __forceinline__ void gather_levels_x2(const GridDev& g, const float (&xa)[3], const float (&xb)[3], bool ina, bool inb,
@@ -310,7 +230,7 @@ __device__ __forceinline__ void gather_levels_x2(const GridDev& g, const float (
 // A C=8 row is 32 bytes.  "lane = sample, two LDG.128 per corner" costs 2 L1 tag cycles per distinct 128-byte line per
 // request (tools/l1_gather.cu), with up to 32 lines per request.  Here 4 lanes share a sample, each fetching 8 bytes (2 of
 // the 8 channels) of every corner row: a request covers 8 samples x 4 quarter rows = 8 lines at 1 cycle per line.
-// One level of grid g at point x: this lane's channel pair (2*part, 2*part+1), blended exactly like encode_level.
+// One level of grid g at point x: this lane's channel pair (2*part, 2*part+1), blended in the reference kernel's corner order.
 __device__ __forceinline__ void quarter_level(const GridDev& g, int l, const float (&x)[3], int part, float& o0, float& o1) {
     const uint32_t res = g.res[l];
     const uint32_t hmask = g.hmask[l];
