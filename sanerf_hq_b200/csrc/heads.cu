@@ -157,21 +157,26 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
     };
     // D[:, part*128 .. +128) -> leaky_relu -> bf16 hi/lo -> A columns of the next layer
     auto epilogue_to_a = [&] {
+        // two tcgen05.ld in flight per step: the TMEM read latency of one 16-column group hides behind the other's math
 #pragma unroll 1
-        for (int grp = 0; grp < 8; grp++) {
-            uint32_t t[16];
-            tc::tmem_ld16(d_rw + part * 128 + grp * 16, t);
+        for (int grp = 0; grp < 8; grp += 2) {
+            uint32_t t0[16], t1[16];
+            tc::tmem_ld16(d_rw + part * 128 + grp * 16, t0);
+            tc::tmem_ld16(d_rw + part * 128 + grp * 16 + 16, t1);
             tc::tmem_ld_wait();
-            float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const float x = __uint_as_float(t[i]);
-                v[i] = x > 0.f ? x : 0.01f * x;   // F.leaky_relu default slope (network.py:66)
+            for (int h = 0; h < 2; h++) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float x = __uint_as_float(h ? t1[i] : t0[i]);
+                    v[i] = x > 0.f ? x : 0.01f * x;   // F.leaky_relu default slope (network.py:66)
+                }
+                uint32_t hi[8], lo[8];
+                pack_split16(v, hi, lo);
+                tc::tmem_st8(a_rw + part * 64 + (grp + h) * 8, hi);
+                tc::tmem_st8(a_rw + kColsAlo + part * 64 + (grp + h) * 8, lo);
             }
-            uint32_t hi[8], lo[8];
-            pack_split16(v, hi, lo);
-            tc::tmem_st8(a_rw + part * 64 + grp * 8, hi);
-            tc::tmem_st8(a_rw + kColsAlo + part * 64 + grp * 8, lo);
         }
         tc::tmem_st_wait();
     };
@@ -374,20 +379,24 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
     // D[:, part*128 .. +128) + bias -> leaky_relu -> bf16 hi/lo -> A columns of the next layer
     auto epilogue_to_a = [&](const float* __restrict__ bias) {
 #pragma unroll 1
-        for (int grp = 0; grp < 8; grp++) {
-            uint32_t t[16];
-            tc::tmem_ld16(d_rw + part * 128 + grp * 16, t);
+        for (int grp = 0; grp < 8; grp += 2) {
+            uint32_t t0[16], t1[16];
+            tc::tmem_ld16(d_rw + part * 128 + grp * 16, t0);
+            tc::tmem_ld16(d_rw + part * 128 + grp * 16 + 16, t1);
             tc::tmem_ld_wait();
-            float v[16];
 #pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const float x = __uint_as_float(t[i]) + __ldg(bias + part * 128 + grp * 16 + i);
-                v[i] = x > 0.f ? x : 0.01f * x;
+            for (int h = 0; h < 2; h++) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const float x = __uint_as_float(h ? t1[i] : t0[i]) + __ldg(bias + part * 128 + (grp + h) * 16 + i);
+                    v[i] = x > 0.f ? x : 0.01f * x;
+                }
+                uint32_t hi[8], lo[8];
+                pack_split16(v, hi, lo);
+                tc::tmem_st8(a_rw + part * 64 + (grp + h) * 8, hi);
+                tc::tmem_st8(a_rw + kColsAlo + part * 64 + (grp + h) * 8, lo);
             }
-            uint32_t hi[8], lo[8];
-            pack_split16(v, hi, lo);
-            tc::tmem_st8(a_rw + part * 64 + grp * 8, hi);
-            tc::tmem_st8(a_rw + kColsAlo + part * 64 + grp * 8, lo);
         }
         tc::tmem_st_wait();
     };
