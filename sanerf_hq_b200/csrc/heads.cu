@@ -88,8 +88,8 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_col, uin
 __global__ void __launch_bounds__(kHeadThreads, 1)
     mask_mlp_kernel(const float* __restrict__ mask_in, const float* __restrict__ weights, const __nv_bfloat16* __restrict__ img,
                     float* __restrict__ logits, uint32_t n_tiles, uint32_t n_rays, uint32_t n_inst) {
-    extern __shared__ __align__(128) uint8_t smem[];   // [2 stages x 64 KB][layer-2 image 16 KB]
-    __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done, bar_w2;
+    extern __shared__ __align__(128) uint8_t smem[];   // [2 stages x 64 KB][layer-2 image 16 KB][input tile 143 x 128 fp32]
+    __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done, bar_w2, bar_in;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, part = warp >> 2;
     const uint32_t stage_saddr = tc::smem_u32(smem), w2_saddr = stage_saddr + 2 * kStageBytes;
@@ -102,6 +102,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         }
         tc::mbar_init(&bar_done, 1);
         tc::mbar_init(&bar_w2, 1);
+        tc::mbar_init(&bar_in, 1);
         tc::fence_mbar_init();
         tc::mbar_expect_tx(&bar_w2, kImg2 * 2);
         tc::tma_load_1d(w2_saddr, img + kOff2, kImg2 * 2, &bar_w2);
@@ -181,10 +182,22 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         tc::tmem_st_wait();
     };
 
-    if (tid == 0 && total_chunks) load_chunk(0);
+    // The per-tile input block ([143][128] fp32, contiguous) is prefetched by TMA into shared memory one tile ahead: the bulk
+    // copy of tile i+1 is issued as soon as tile i has been staged into TMEM and overlaps all of tile i's MMAs.
+    const float* xin = reinterpret_cast<const float*>(smem + 2 * kStageBytes + kImg2 * 2);
+    const uint32_t xin_saddr = stage_saddr + 2 * kStageBytes + kImg2 * 2;
+    constexpr uint32_t kInBytes = kMaskK0 * 128 * sizeof(float);
+    uint32_t ph_in = 0;
+    if (tid == 0 && total_chunks) {
+        load_chunk(0);
+        tc::mbar_expect_tx(&bar_in, kInBytes);
+        tc::tma_load_1d(xin_saddr, mask_in + (size_t)blockIdx.x * kMaskK0 * 128, kInBytes, &bar_in);
+    }
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- layer-0 input: this thread's row, k in [0,64) (part 0) or [64,144) (part 1) ---------------------------
-        const float* src = mask_in + (size_t)tile * kMaskK0 * 128 + q * 32 + lane;
+        tc::mbar_wait(&bar_in, ph_in);
+        ph_in ^= 1;
+        const float* src = xin + q * 32 + lane;
         const int k_begin = part ? 64 : 0, n_grp = part ? 5 : 4;
 #pragma unroll 1
         for (int grp = 0; grp < n_grp; grp++) {
@@ -192,7 +205,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
 #pragma unroll
             for (int i = 0; i < 16; i++) {
                 const int k = k_begin + grp * 16 + i;
-                v[i] = k < kMaskK0 ? __ldg(src + (size_t)k * 128) : 0.f;
+                v[i] = k < kMaskK0 ? src[k * 128] : 0.f;
             }
             uint32_t hi[8], lo[8];
             pack_split16(v, hi, lo);
@@ -202,6 +215,11 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         tc::tmem_st_wait();
         // ---- layer 0: 143(+1) -> 256 ------------------------------------------------------------------------------
         run_chunks(kNCh0, [&](int c, uint32_t saddr) { issue_chunk<kMaskH, kCh0>(d_mma, a_mma + c * (kCh0 / 2), saddr, c > 0 ? 1u : 0u); });
+        // every thread has passed the barrier inside run_chunks after reading its input row: the buffer can take the next tile
+        if (tid == 0 && tile + gridDim.x < n_tiles) {
+            tc::mbar_expect_tx(&bar_in, kInBytes);
+            tc::tma_load_1d(xin_saddr, mask_in + (size_t)(tile + gridDim.x) * kMaskK0 * 128, kInBytes, &bar_in);
+        }
         epilogue_to_a();
         // ---- layer 1: 256 -> 256 --------------------------------------------------------------------------------------
         run_chunks(kNCh1, [&](int c, uint32_t saddr) { issue_chunk<kMaskH, kCh1>(d_mma, a_mma + c * (kCh1 / 2), saddr, c > 0 ? 1u : 0u); });
@@ -519,7 +537,7 @@ int sanerf_mask_mlp(const float* mask_in_tiled, const float* weights, const floa
     cudaStream_t st = (cudaStream_t)stream;
     __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(workspace);
     mask_prepare_kernel<<<64, 256, 0, st>>>(w0, w1, w2, n_inst, img);
-    const size_t smem = 2 * (size_t)kStageBytes + (size_t)kImg2 * 2;
+    const size_t smem = 2 * (size_t)kStageBytes + (size_t)kImg2 * 2 + (size_t)kMaskK0 * 128 * sizeof(float);
     if (cudaFuncSetAttribute(mask_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return SANERF_E_SMEM;
