@@ -314,17 +314,20 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
                       const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ b3, const float* __restrict__ b4,
                       const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ out, uint32_t n_tiles, uint32_t n_rays) {
     extern __shared__ __align__(128) uint8_t smem[];   // [2 stages x 64 KB][input tile 128 x 163 fp32]
-    __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done;
+    __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done, bar_in;
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, part = warp >> 2;
     const uint32_t stage_saddr = tc::smem_u32(smem);
-    float* xt = reinterpret_cast<float*>(smem + 2 * kStageBytes);
+    const float* xt = reinterpret_cast<const float*>(smem + 2 * kStageBytes);
+    const uint32_t xt_saddr = stage_saddr + 2 * kStageBytes;
+    constexpr uint32_t kInBytes = 128 * kSamIn * sizeof(float);
     if (tid == 0) {
         for (int i = 0; i < 2; i++) {
             tc::mbar_init(&bar_full[i], 1);
             tc::mbar_init(&bar_free[i], 1);
         }
         tc::mbar_init(&bar_done, 1);
+        tc::mbar_init(&bar_in, 1);
         tc::fence_mbar_init();
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
@@ -419,16 +422,17 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         tc::tmem_st_wait();
     };
 
-    if (tid == 0 && total_chunks) load_chunk(0);
+    // The input tile ([128,163] fp32, 83 KB, contiguous; the buffer is padded to whole tiles) is prefetched by TMA one tile
+    // ahead: the copy of tile i+1 starts right after tile i's second (skip-connection) use of the buffer.
+    uint32_t ph_in = 0;
+    if (tid == 0 && total_chunks) {
+        load_chunk(0);
+        tc::mbar_expect_tx(&bar_in, kInBytes);
+        tc::tma_load_1d(xt_saddr, sam_in + (size_t)blockIdx.x * 128 * kSamIn, kInBytes, &bar_in);
+    }
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- input tile [128,163] fp32 -> shared memory (coalesced 16-byte copies; the buffer is padded to whole tiles) ----
-        __syncthreads();   // the previous tile's readers of xt are done
-        {
-            const float4* src = reinterpret_cast<const float4*>(sam_in + (size_t)tile * 128 * kSamIn);
-            float4* dst = reinterpret_cast<float4*>(xt);
-            for (int i = tid; i < 128 * kSamIn / 4; i += kHeadThreads) dst[i] = __ldg(src + i);
-        }
-        __syncthreads();
+        tc::mbar_wait(&bar_in, ph_in);
+        ph_in ^= 1;
         stage_input();
         run_chunks(3);          // layer 0: 163 -> 256
         epilogue_to_a(b0);
@@ -437,6 +441,10 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         run_chunks(4);          // layer 2, hidden part (columns 0..255 of the [256,419] weight); its MMAs have read A when this returns
         stage_input();
         run_chunks(3);          // layer 2, skip part (columns 256..418), accumulates onto D
+        if (tid == 0 && tile + gridDim.x < n_tiles) {   // all threads passed run_chunks' barrier after their last read of xt
+            tc::mbar_expect_tx(&bar_in, kInBytes);
+            tc::tma_load_1d(xt_saddr, sam_in + (size_t)(tile + gridDim.x) * 128 * kSamIn, kInBytes, &bar_in);
+        }
         epilogue_to_a(b2);
         run_chunks(4);          // layer 3
         epilogue_to_a(b3);
