@@ -176,8 +176,10 @@ typedef struct {
                                        (renderer.py:361-367); requires model->s_grid */
     float *mask_in;                 /* optional [N,32, 8*Lm+15] (143): per-sample cat[m_grid(x), geo_feat], the mask_mlp
                                        input (renderer.py:304-305, 378); requires model->m_grid */
-    uint32_t mask_in_tiled;         /* 0: row-major as above; 1: tile-transposed [ceil(N*32/128)][K][128] (row = ray*32+sample),
-                                       the layout sanerf_mask_mlp consumes; N must then start at a multiple of 4 rays */
+    uint32_t mask_in_tiled;         /* 0: row-major as above; 1: the same values tile-transposed [ceil(N*32/128)][K][128]
+                                       (row = ray*32+sample); 2: record mode for sanerf_mask_head, which gathers m_grid itself:
+                                       mask_in is [ceil(N*32/128)][18][128] = per sample the point in [0,1]^3 (3) and geo_feat
+                                       (15), model->m_grid is not read.  N must start at a multiple of 4 rays for 1 and 2. */
     /* optional debug / parity taps (NULL to skip) */
     int16_t *inds0;                 /* [N,65]  searchsorted result of the 1st sample_pdf */
     int16_t *inds1;                 /* [N,33]  of the 2nd */
@@ -211,15 +213,16 @@ int sanerf_render_launch_count(const sanerf_model_t *model, const sanerf_render_
 int sanerf_sample_pdf(const float *bins, const float *weights, const float *u, uint32_t N, uint32_t T0,
                       uint32_t T, float *new_bins, int16_t *inds, sanerf_stream_t stream);
 
-/* Object (instance-mask) head on the tensor cores: replaces `mask_mlp(cat[masks, geo_feat])` + the weighted sum over samples
- * (nerf/renderer.py:376-385; SkipConnMLP 143 -> 256 -> 256 -> n_inst, no bias, leaky_relu 0.01, network.py:119-123).
- * mask_in_tiled: tile-transposed per-sample inputs written by sanerf_render (mask_in_tiled = 1); weights [n_rays,32] = the
- * final-stage compositing weights; w0 [256,143], w1 [256,256], w2 [n_inst,256] in nn.Linear layout; workspace: device
- * scratch of sanerf_mask_mlp_workspace_bytes() for the split-precision operand images; logits [n_rays,n_inst].
- * bf16 hi/lo split operands, fp32 accumulation (error ~1e-5 relative).  n_inst <= 16. */
-size_t sanerf_mask_mlp_workspace_bytes(void);
-int sanerf_mask_mlp(const float *mask_in_tiled, const float *weights, const float *w0, const float *w1, const float *w2,
-                    uint32_t n_inst, uint32_t n_rays, void *workspace, float *logits, sanerf_stream_t stream);
+/* Object (instance-mask) head on the tensor cores: replaces `m_grid(xyzs)`, `mask_mlp(cat[masks, geo_feat])` and the weighted
+ * sum over samples (nerf/renderer.py:304-305, 376-385; SkipConnMLP 143 -> 256 -> 256 -> n_inst, no bias, leaky_relu 0.01,
+ * network.py:119-123).  records: the per-sample (point, geo_feat) records written by sanerf_render with mask_in_tiled = 2,
+ * [ceil(n_rays*32/128)][18][128]; weights [n_rays,32] = the final-stage compositing weights; m_grid: the object feature grid
+ * (HOST struct, 16 levels x 8 channels), gathered inside the kernel by producer warps while the MMAs run; w0 [256,143],
+ * w1 [256,256], w2 [n_inst,256] in nn.Linear layout; workspace: device scratch of sanerf_mask_head_workspace_bytes() for the
+ * split-precision operand images; logits [n_rays,n_inst].  bf16 hi/lo split operands, fp32 accumulation.  n_inst <= 16. */
+size_t sanerf_mask_head_workspace_bytes(void);
+int sanerf_mask_head(const float *records, const float *weights, const sanerf_grid_t *m_grid, const float *w0, const float *w1,
+                     const float *w2, uint32_t n_inst, uint32_t n_rays, void *workspace, float *logits, sanerf_stream_t stream);
 
 /* SAM feature head on the tensor cores: samvit = LayerNorm(SkipConnMLP(f)) per ray (nerf/renderer.py:361-369,
  * nerf/network.py:113-116): sam_in [n_rays (buffer padded to a multiple of 128 rows), 163] row-major as written by

@@ -54,8 +54,8 @@ PROTOTYPES = {
     "sanerf_render_launch_count": [ctypes.POINTER(ModelT), ctypes.POINTER(RenderArgsT)],
     "sanerf_sample_pdf": [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp],
     "sanerf_mlp3_tc": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp],
-    "sanerf_mask_mlp_workspace_bytes": [],
-    "sanerf_mask_mlp": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp],
+    "sanerf_mask_head_workspace_bytes": [],
+    "sanerf_mask_head": [_vp, _vp, ctypes.POINTER(GridT), _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp],
     "sanerf_samvit_mlp_workspace_bytes": [],
     "sanerf_samvit_mlp": [_vp, _vp * 5, _vp * 5, _vp, _vp, _u32, _vp, _vp, _vp],
     "sanerf_abi_version": [],

@@ -21,6 +21,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "grid_dev.cuh"
 #include "tc.cuh"
 
 namespace sanerf {
@@ -85,13 +86,21 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_col, uin
     }
 }
 
-__global__ void __launch_bounds__(kHeadThreads, 1)
-    mask_mlp_kernel(const float* __restrict__ mask_in, const float* __restrict__ weights, const __nv_bfloat16* __restrict__ img,
-                    float* __restrict__ logits, uint32_t n_tiles, uint32_t n_rays, uint32_t n_inst) {
+// Warps 0..7 are the tensor-core side (as in samvit_mlp_kernel below); warps 8..15 are PRODUCERS: while the MMAs of tile i run
+// they gather m_grid (16 levels x 8 corners of 32-byte rows, quarter-row loads) for the 128 samples of tile i+1 straight into
+// the shared-memory input tile [143][128], from the 18-float records (point, geo_feat) the render kernel left per sample.
+// The gather (L1 / LSU bound) and the MLP (tensor / epilogue bound) therefore overlap on the same SM, and the 572-byte
+// per-sample input never exists in HBM.
+constexpr int kMaskThreads = 2 * kHeadThreads, kRecK = 18;
+
+__global__ void __launch_bounds__(kMaskThreads, 1)
+    mask_head_kernel(const float* __restrict__ rec, const float* __restrict__ weights, const __grid_constant__ GridDev mg,
+                     const __nv_bfloat16* __restrict__ img, float* __restrict__ logits, uint32_t n_tiles, uint32_t n_rays, uint32_t n_inst) {
     extern __shared__ __align__(128) uint8_t smem[];   // [2 stages x 64 KB][layer-2 image 16 KB][input tile 143 x 128 fp32]
-    __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done, bar_w2, bar_in;
+    __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done, bar_w2, bar_in_full, bar_in_free;
     __shared__ uint32_t tmem_base_s;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, part = warp >> 2;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, part = (warp >> 2) & 1;
+    const bool producer = warp >= 8;
     const uint32_t stage_saddr = tc::smem_u32(smem), w2_saddr = stage_saddr + 2 * kStageBytes;
 
     // barriers + tensor memory; the resident layer-2 image arrives by TMA bulk copy
@@ -102,7 +111,8 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         }
         tc::mbar_init(&bar_done, 1);
         tc::mbar_init(&bar_w2, 1);
-        tc::mbar_init(&bar_in, 1);
+        tc::mbar_init(&bar_in_full, kHeadThreads);   // every producer thread arrives
+        tc::mbar_init(&bar_in_free, kHeadThreads);   // every consumer thread arrives
         tc::fence_mbar_init();
         tc::mbar_expect_tx(&bar_w2, kImg2 * 2);
         tc::tma_load_1d(w2_saddr, img + kOff2, kImg2 * 2, &bar_w2);
@@ -133,7 +143,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
     // bytes, issue the MMAs, commit, and refill the stage the previous chunk has released with the chunk after this one.
     auto run_chunks = [&](int n_chunks, auto&& issue) {
         tc::fence_before_sync();          // this thread's tcgen05.st / tcgen05.ld are ordered before the barrier
-        __syncthreads();
+        tc::named_barrier(1, kHeadThreads);   // the 8 tensor-core-side warps only
         if (tid == 0) {
             tc::fence_after_sync();
             for (int c = 0; c < n_chunks; c++, g++) {
@@ -182,20 +192,52 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         tc::tmem_st_wait();
     };
 
-    // The per-tile input block ([143][128] fp32, contiguous) is prefetched by TMA into shared memory one tile ahead: the bulk
-    // copy of tile i+1 is issued as soon as tile i has been staged into TMEM and overlaps all of tile i's MMAs.
-    const float* xin = reinterpret_cast<const float*>(smem + 2 * kStageBytes + kImg2 * 2);
-    const uint32_t xin_saddr = stage_saddr + 2 * kStageBytes + kImg2 * 2;
-    constexpr uint32_t kInBytes = kMaskK0 * 128 * sizeof(float);
+    float* xin = reinterpret_cast<float*>(smem + 2 * kStageBytes + kImg2 * 2);   // [143][128] input tile, filled by the producers
     uint32_t ph_in = 0;
-    if (tid == 0 && total_chunks) {
-        load_chunk(0);
-        tc::mbar_expect_tx(&bar_in, kInBytes);
-        tc::tma_load_1d(xin_saddr, mask_in + (size_t)blockIdx.x * kMaskK0 * 128, kInBytes, &bar_in);
-    }
+    if (producer) {
+        // ---- producer warps: build the input tile of every tile of this CTA, one tile ahead of the tensor-core side --------
+        const int pw = warp - 8, s8 = lane >> 2, qp = lane & 3, ptid = tid - kHeadThreads;
+        const int rowA = 8 * pw + s8, rowB = 64 + rowA;    // two samples per lane quad, gathered together (16 loads in flight)
+        bool first = true;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const float* r = rec + (size_t)tile * kRecK * 128;
+            float xa[3], xb[3];
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                xa[d] = __ldg(r + d * 128 + rowA);
+                xb[d] = __ldg(r + d * 128 + rowB);
+            }
+            bool ina = true, inb = true;   // points outside [0,1]^3 give zero features (gridencoder.cu:105-130)
+#pragma unroll
+            for (int d = 0; d < 3; d++) {
+                ina &= !(xa[d] < 0.f || xa[d] > 1.f);
+                inb &= !(xb[d] < 0.f || xb[d] > 1.f);
+            }
+            if (!first) {                  // the tensor-core side has copied the previous tile out of the buffer
+                tc::mbar_wait(&bar_in_free, ph_in);
+                ph_in ^= 1;
+            }
+            first = false;
+#pragma unroll 1
+            for (int l = 0; l < 16; l++) {
+                float a0, a1, b0, b1;
+                quarter_level(mg, l, xa, qp, a0, a1);
+                quarter_level(mg, l, xb, qp, b0, b1);
+                float* d0 = xin + (8 * l + 2 * qp) * 128;
+                d0[rowA] = ina ? a0 : 0.f;
+                d0[128 + rowA] = ina ? a1 : 0.f;
+                d0[rowB] = inb ? b0 : 0.f;
+                d0[128 + rowB] = inb ? b1 : 0.f;
+            }
+            for (int i = ptid; i < 15 * 128; i += kHeadThreads) xin[128 * 128 + i] = __ldg(r + 3 * 128 + i);   // geo_feat rows
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_in_full)) : "memory");
+        }
+    } else {
+    // ---- tensor-core side -------------------------------------------------------------------------------------------
+    if (tid == 0 && total_chunks) load_chunk(0);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         // ---- layer-0 input: this thread's row, k in [0,64) (part 0) or [64,144) (part 1) ---------------------------
-        tc::mbar_wait(&bar_in, ph_in);
+        tc::mbar_wait(&bar_in_full, ph_in);
         ph_in ^= 1;
         const float* src = xin + q * 32 + lane;
         const int k_begin = part ? 64 : 0, n_grp = part ? 5 : 4;
@@ -215,18 +257,16 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         tc::tmem_st_wait();
         // ---- layer 0: 143(+1) -> 256 ------------------------------------------------------------------------------
         run_chunks(kNCh0, [&](int c, uint32_t saddr) { issue_chunk<kMaskH, kCh0>(d_mma, a_mma + c * (kCh0 / 2), saddr, c > 0 ? 1u : 0u); });
-        // every thread has passed the barrier inside run_chunks after reading its input row: the buffer can take the next tile
-        if (tid == 0 && tile + gridDim.x < n_tiles) {
-            tc::mbar_expect_tx(&bar_in, kInBytes);
-            tc::tma_load_1d(xin_saddr, mask_in + (size_t)(tile + gridDim.x) * kMaskK0 * 128, kInBytes, &bar_in);
-        }
+        // every tensor-core-side thread has passed the barrier inside run_chunks after reading its input row: hand the buffer
+        // back to the producers (who are already gathering... into it as soon as all 256 arrivals are in)
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_in_free)) : "memory");
         epilogue_to_a();
         // ---- layer 1: 256 -> 256 --------------------------------------------------------------------------------------
         run_chunks(kNCh1, [&](int c, uint32_t saddr) { issue_chunk<kMaskH, kCh1>(d_mma, a_mma + c * (kCh1 / 2), saddr, c > 0 ? 1u : 0u); });
         epilogue_to_a();
         // ---- layer 2: 256 -> n_inst (16 output columns), resident image ----------------------------------------------
         tc::fence_before_sync();
-        __syncthreads();
+        tc::named_barrier(1, kHeadThreads);
         if (tid == 0) {
             tc::fence_after_sync();
             if (tile == blockIdx.x) tc::mbar_wait(&bar_w2, 0);   // first use: the resident image has landed
@@ -254,8 +294,9 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
                 }
             }
         }
-        // the next tile's first barrier (inside consume) orders these TMEM reads before the next MMAs overwrite D
+        // the next tile's first barrier (inside run_chunks) orders these TMEM reads before the next MMAs overwrite D
     }
+    }   // tensor-core side
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tm, 512);
@@ -535,18 +576,21 @@ using namespace sanerf;
 
 extern "C" {
 
-size_t sanerf_mask_mlp_workspace_bytes(void) { return (size_t)kImgTotal * sizeof(__nv_bfloat16); }
+size_t sanerf_mask_head_workspace_bytes(void) { return (size_t)kImgTotal * sizeof(__nv_bfloat16); }
 
-int sanerf_mask_mlp(const float* mask_in_tiled, const float* weights, const float* w0, const float* w1, const float* w2, uint32_t n_inst,
-                    uint32_t n_rays, void* workspace, float* logits, sanerf_stream_t stream) {
+int sanerf_mask_head(const float* records, const float* weights, const sanerf_grid_t* m_grid, const float* w0, const float* w1,
+                     const float* w2, uint32_t n_inst, uint32_t n_rays, void* workspace, float* logits, sanerf_stream_t stream) {
     if (n_rays == 0) return 0;
-    if (!mask_in_tiled || !weights || !w0 || !w1 || !w2 || !workspace || !logits) return SANERF_E_NULL;
-    if (n_inst == 0 || n_inst > (uint32_t)kMaskNOut) return SANERF_E_CONFIG;
+    if (!records || !weights || !m_grid || !w0 || !w1 || !w2 || !workspace || !logits) return SANERF_E_NULL;
+    if (n_inst == 0 || n_inst > (uint32_t)kMaskNOut || m_grid->num_levels != 16) return SANERF_E_CONFIG;
+    GridDev mg;
+    int rc = fill_grid(mg, *m_grid, 8);
+    if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(workspace);
     mask_prepare_kernel<<<64, 256, 0, st>>>(w0, w1, w2, n_inst, img);
     const size_t smem = 2 * (size_t)kStageBytes + (size_t)kImg2 * 2 + (size_t)kMaskK0 * 128 * sizeof(float);
-    if (cudaFuncSetAttribute(mask_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(mask_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return SANERF_E_SMEM;
     }
@@ -554,8 +598,8 @@ int sanerf_mask_mlp(const float* mask_in_tiled, const float* weights, const floa
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t n_tiles = div_up(n_rays, 4u);
-    mask_mlp_kernel<<<n_tiles < (uint32_t)sms ? n_tiles : (uint32_t)sms, kHeadThreads, smem, st>>>(mask_in_tiled, weights, img, logits, n_tiles,
-                                                                                                  n_rays, n_inst);
+    mask_head_kernel<<<n_tiles < (uint32_t)sms ? n_tiles : (uint32_t)sms, kMaskThreads, smem, st>>>(records, weights, mg, img, logits, n_tiles,
+                                                                                                    n_rays, n_inst);
     return check_launch();
 }
 

@@ -26,6 +26,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "grid_dev.cuh"
 #include "tc.cuh"
 
 namespace sanerf {
@@ -45,18 +46,6 @@ constexpr bool kShareSlots = kGroups > 4;     // more groups than 128-column TME
 constexpr int kThreads = kWarps * 32;
 constexpr int kMaxT = 128;              // samples of the widest stage
 constexpr unsigned kFull = 0xffffffffu;
-
-// ---- device-side model description (kernel parameter, constant bank) -------------------------
-struct GridDev {
-    const float* emb;
-    uint32_t L, C;
-    uint32_t off[SANERF_MAX_LEVELS];    // row offset of the level
-    uint32_t res[SANERF_MAX_LEVELS];    // kernel-side resolution
-    uint32_t hmask[SANERF_MAX_LEVELS];  // rows-1 for hashed levels (rows is a power of two), 0 = dense
-    const void* base[SANERF_MAX_LEVELS];  // emb + off[l]*C: first row of the level (saves the per-load offset add)
-    float resf[SANERF_MAX_LEVELS];        // (float)res, (float)(res-1)
-    float topf[SANERF_MAX_LEVELS];
-};
 
 struct RenderParams {
     GridDev prop[2], grid, sgrid, mgrid;
@@ -145,14 +134,6 @@ __device__ __forceinline__ void contract3(float& x, float& y, float& z) {
     z = __fmul_rn(z, idx == 2 ? big : inv);
 }
 
-// floor of a clamped grid coordinate 0 <= pos < 2^22 without the conversion unit (FRND / F2I run on the quarter-rate XU pipe):
-// pos + 2^23 rounded toward zero has an ulp of 1, so its low mantissa bits ARE floor(pos); both results are exact.
-__device__ __forceinline__ void floor_split(float pos, uint32_t& cell, float& frac) {
-    const float t = __fadd_rz(pos, 8388608.0f);
-    cell = __float_as_uint(t) & 0x007fffffu;
-    frac = pos - (t - 8388608.0f);
-}
-
 // ---- software-pipelined C=2 gathers ------------------------------------------------------------------------------------
 // A level is split into `issue` (cell lookup + the 8 row loads) and `finish` (trilinear blend, same FMA order as
 // the reference kernel, gridencoder.cu:170-195); the callers keep one or two levels of loads in flight per thread so the L1/L2
@@ -224,49 +205,6 @@ __device__ __forceinline__ void gather_levels_x2(const GridDev& g, const float (
         fb[2 * l] = inb ? b0 : 0.f;
         fb[2 * l + 1] = inb ? b1 : 0.f;
     }
-}
-
-// ---- C=8 feature grids: quarter-row gathers -------------------------------------------------------------------------
-// A C=8 row is 32 bytes.  "lane = sample, two LDG.128 per corner" costs 2 L1 tag cycles per distinct 128-byte line per
-// request (tools/l1_gather.cu), with up to 32 lines per request.  Here 4 lanes share a sample, each fetching 8 bytes (2 of
-// the 8 channels) of every corner row: a request covers 8 samples x 4 quarter rows = 8 lines at 1 cycle per line.
-// One level of grid g at point x: this lane's channel pair (2*part, 2*part+1), blended in the reference kernel's corner order.
-__device__ __forceinline__ void quarter_level(const GridDev& g, int l, const float (&x)[3], int part, float& o0, float& o1) {
-    const uint32_t res = g.res[l];
-    const uint32_t hmask = g.hmask[l];
-    const float2* __restrict__ rows = reinterpret_cast<const float2*>(g.base[l]) + part;   // 4 float2 per row
-    const float resf = g.resf[l], top = g.topf[l];
-    uint32_t b0[3], b1[3];
-    float f[3];
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-        float pos = fminf(fmaxf(__fmaf_rn(x[d], resf, -0.5f), 0.0f), top);
-        floor_split(pos, b0[d], f[d]);
-        b1[d] = min(b0[d] + 1, res - 1);
-    }
-    float2 v[8];
-    if (hmask == 0) {
-        const uint32_t y0 = b0[1] * res, y1 = b1[1] * res, z0 = b0[2] * res * res, z1 = b1[2] * res * res;
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = __ldg(rows + 4 * (((i & 1) ? b1[0] : b0[0]) + ((i & 2) ? y1 : y0) + ((i & 4) ? z1 : z0)));
-    } else {
-        const uint32_t x0 = b0[0] & hmask, x1 = b1[0] & hmask;
-        const uint32_t y0 = (b0[1] * 2654435761u) & hmask, y1 = (b1[1] * 2654435761u) & hmask;
-        const uint32_t z0 = (b0[2] * 805459861u) & hmask, z1 = (b1[2] * 805459861u) & hmask;
-#pragma unroll
-        for (int i = 0; i < 8; i++) v[i] = __ldg(rows + 4 * (((i & 1) ? x1 : x0) ^ ((i & 2) ? y1 : y0) ^ ((i & 4) ? z1 : z0)));
-    }
-    float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; i++) {
-        float ww = (i & 1) ? f[0] : 1 - f[0];
-        ww *= (i & 2) ? f[1] : 1 - f[1];
-        ww *= (i & 4) ? f[2] : 1 - f[2];
-        a0 = __fmaf_rn(ww, v[i].x, a0);
-        a1 = __fmaf_rn(ww, v[i].y, a1);
-    }
-    o0 = a0;
-    o1 = a1;
 }
 
 // y[n] = sum_k W[n][k] x[k], W in shared memory as [N][KP] (KP = K rounded up to 4, zero padded);
@@ -821,43 +759,53 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         }
         // ---- object head input: per-sample cat[m_grid(x), geo_feat] (renderer.py:304-305, 378) ---
         if constexpr (MASK) if (active) {
-            const int nl = (int)p.mgrid.L;
-            // row-major [ray,32,K] (reference tensor layout) or tile-transposed [row/128][K][128] for the tensor-core head
-            // (heads.cu): there lane <-> consecutive row, so every store below is one coalesced 128-byte line per warp
-            const int K = 8 * nl + 15;
-            const size_t kstride = p.mask_tiled ? 128 : 1;
-            auto row_ptr = [&](int sample) {
-                const size_t row = (size_t)ray * 32 + sample;
-                return p.mask_tiled ? p.mask_in + (row >> 7) * (size_t)K * 128 + (row & 127) : p.mask_in + row * K;
-            };
-            // m_grid(x) per sample with quarter-row gathers (see quarter_level): lanes (s8, part) = (sample mod 8, channel pair),
-            // four passes of 8 samples; every lane writes its two channels of its pass's sample
-            {
-                const int s8 = lane >> 2, part = lane & 3;
-                float xs[4][3];
-                bool ins[4];
+            if (p.mask_tiled == 2) {
+                // record mode for the tensor-core object head (heads.cu), which gathers m_grid itself while its MMAs run:
+                // per sample only the point (3) and geo_feat (15), tile-transposed [row/128][18][128] (coalesced 128-B stores)
+                const size_t row = (size_t)ray * 32 + home;
+                float* dst = p.mask_in + (row >> 7) * (size_t)(18 * 128) + (row & 127);
 #pragma unroll
-                for (int ps = 0; ps < 4; ps++) {
-                    const int srcl = 8 * ps + s8;
+                for (int d = 0; d < 3; d++) dst[d * 128] = x01[d];
 #pragma unroll
-                    for (int d = 0; d < 3; d++) xs[ps][d] = __shfl_sync(kFull, x01[d], srcl);
-                    ins[ps] = __shfl_sync(kFull, inside ? 1 : 0, srcl) != 0;
-                }
-#pragma unroll 1
-                for (int l = 0; l < nl; l++) {
+                for (int c = 0; c < 15; c++) dst[(3 + c) * 128] = f16[c + 1];
+            } else {
+                const int nl = (int)p.mgrid.L;
+                // row-major [ray,32,K] (reference tensor layout) or tile-transposed [row/128][K][128]
+                const int K = 8 * nl + 15;
+                const size_t kstride = p.mask_tiled ? 128 : 1;
+                auto row_ptr = [&](int sample) {
+                    const size_t row = (size_t)ray * 32 + sample;
+                    return p.mask_tiled ? p.mask_in + (row >> 7) * (size_t)K * 128 + (row & 127) : p.mask_in + row * K;
+                };
+                // m_grid(x) per sample with quarter-row gathers (see quarter_level): lanes (s8, part) = (sample mod 8, channel
+                // pair), four passes of 8 samples; every lane writes its two channels of its pass's sample
+                {
+                    const int s8 = lane >> 2, part = lane & 3;
+                    float xs[4][3];
+                    bool ins[4];
 #pragma unroll
                     for (int ps = 0; ps < 4; ps++) {
-                        float o0, o1;
-                        quarter_level(p.mgrid, l, xs[ps], part, o0, o1);
-                        float* dst = row_ptr(8 * ps + s8) + (size_t)(8 * l + 2 * part) * kstride;
-                        dst[0] = ins[ps] ? o0 : 0.f;
-                        dst[kstride] = ins[ps] ? o1 : 0.f;
+                        const int srcl = 8 * ps + s8;
+#pragma unroll
+                        for (int d = 0; d < 3; d++) xs[ps][d] = __shfl_sync(kFull, x01[d], srcl);
+                        ins[ps] = __shfl_sync(kFull, inside ? 1 : 0, srcl) != 0;
+                    }
+#pragma unroll 1
+                    for (int l = 0; l < nl; l++) {
+#pragma unroll
+                        for (int ps = 0; ps < 4; ps++) {
+                            float o0, o1;
+                            quarter_level(p.mgrid, l, xs[ps], part, o0, o1);
+                            float* dst = row_ptr(8 * ps + s8) + (size_t)(8 * l + 2 * part) * kstride;
+                            dst[0] = ins[ps] ? o0 : 0.f;
+                            dst[kstride] = ins[ps] ? o1 : 0.f;
+                        }
                     }
                 }
-            }
-            float* dst = row_ptr(home);
+                float* dst = row_ptr(home);
 #pragma unroll
-            for (int c = 0; c < 15; c++) dst[(8 * nl + c) * kstride] = f16[c + 1];
+                for (int c = 0; c < 15; c++) dst[(8 * nl + c) * kstride] = f16[c + 1];
+            }
         }
         __syncwarp();
     }
@@ -886,37 +834,6 @@ __global__ void __launch_bounds__(256) sample_pdf_kernel(const float* __restrict
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-static int fill_grid(GridDev& g, const sanerf_grid_t& s, uint32_t C_expected) {
-    g.emb = s.embeddings;
-    g.L = s.num_levels;
-    g.C = s.level_dim;
-    if (!s.embeddings || s.num_levels == 0 || s.num_levels > SANERF_MAX_LEVELS || s.level_dim != C_expected) return SANERF_E_CONFIG;
-    for (uint32_t l = 0; l < s.num_levels; l++) {
-        const uint32_t rows = s.offset[l + 1] - s.offset[l], res = s.res[l];
-        if (res < 2 || rows == 0) return SANERF_E_CONFIG;
-        // the reference's dense-vs-hash decision (gridencoder.cu:61-79) for D=3, gridtype hash
-        uint64_t stride = 1;
-        for (int d = 0; d < 3 && stride <= rows; d++) stride *= res;
-        g.off[l] = s.offset[l];
-        g.res[l] = res;
-        g.base[l] = s.embeddings + (size_t)s.offset[l] * s.level_dim;
-        g.resf[l] = (float)res;
-        g.topf[l] = (float)(res - 1);
-        if (stride <= rows) {
-            g.hmask[l] = 0;  // dense, index < res^3 <= rows
-        } else {
-            if (rows & (rows - 1)) return SANERF_E_CONFIG;  // hashed levels have 2^T rows (grid.py:129)
-            g.hmask[l] = rows - 1;
-        }
-    }
-    for (uint32_t l = s.num_levels; l < SANERF_MAX_LEVELS; l++) {
-        g.off[l] = g.res[l] = g.hmask[l] = 0;
-        g.base[l] = nullptr;
-        g.resf[l] = g.topf[l] = 0.f;
-    }
-    return 0;
-}
-
 template <int PL, int GL, int HG, int HV>
 static int launch_render(const RenderParams& p, bool sam, bool mask, cudaStream_t st) {
     using S = Smem<PL, GL, HG>;
@@ -962,7 +879,7 @@ int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf
     if ((rc = fill_grid(p.grid, m->grid, 2))) return rc;
     const bool sam = a->sam_in != nullptr, mask = a->mask_in != nullptr;
     if (sam) { if ((rc = fill_grid(p.sgrid, m->s_grid, 8))) return rc; } else { p.sgrid = GridDev{}; }
-    if (mask) { if ((rc = fill_grid(p.mgrid, m->m_grid, 8))) return rc; } else { p.mgrid = GridDev{}; }
+    if (mask && a->mask_in_tiled != 2) { if ((rc = fill_grid(p.mgrid, m->m_grid, 8))) return rc; } else { p.mgrid = GridDev{}; }
     for (int i = 0; i < 2; i++) {
         p.prop_w0[i] = m->prop_w0[i];
         p.prop_w1[i] = m->prop_w1[i];

@@ -368,24 +368,25 @@ class NeRFRenderer(nn.Module):
                 results["samvit"] = self._samvit_head(sam_in).view(H, W, -1)
             return results
 
-        # object head.  The per-sample mask_mlp inputs cat[m_grid(x), geo_feat] are written by the fused kernel for a chunk of
-        # rays at a time (bounds the scratch to `chunk`*32*143 floats) and consumed by the tensor-core head (csrc/heads.cu:
-        # mask_mlp 143 -> 256 -> 256 -> n_inst + the weighted sum over samples, ONE launch per chunk).  Other widths than the
-        # reference's default (config #1's small network, n_inst > 16) use the same inputs with the nn.Module MLP.
+        # object head.  Default shapes: the fused kernel leaves an 18-float record (point, geo_feat) per sample and the
+        # tensor-core head (csrc/heads.cu) gathers m_grid, runs mask_mlp 143 -> 256 -> 256 -> n_inst and composites, one launch
+        # per chunk of rays (the chunk bounds the scratch).  Other widths (config #1's small network, n_inst > 16): the fused
+        # kernel writes the full per-sample inputs cat[m_grid(x), geo_feat] and the nn.Module MLP consumes them.
         n_inst = self.opt.n_inst
         logits = torch.empty(N, n_inst, device=device)
         width = self.mask_mlp[0].dim_in
         net = self.mask_mlp[0].net
         tc_head = (width == 143 and len(net) == 3 and net[0].weight.shape == (256, 143) and net[1].weight.shape == (256, 256)
                    and net[2].weight.shape == (n_inst, 256) and n_inst <= 16 and all(l.bias is None for l in net))
-        chunk = max(4, min(-(-N // 4) * 4, 131072 if tc_head else int(getattr(self.opt, "max_ray_batch", 4096)) * 8))
-        mask_in = torch.empty(chunk * 32 * width, device=device)
+        tc_head = tc_head and self.m_grid.num_levels == 16 and self.m_grid.level_dim == 8
+        chunk = max(4, min(-(-N // 4) * 4, 1 << 20 if tc_head else int(getattr(self.opt, "max_ray_batch", 4096)) * 8))
+        mask_in = torch.empty(chunk * 32 * (18 if tc_head else width), device=device)
         w2 = torch.empty(chunk, 32, device=device)
         if tc_head:
             if getattr(self, "_mask_ws", None) is None or self._mask_ws.device != device:
-                self._mask_ws = torch.empty(lib.sanerf_mask_mlp_workspace_bytes(), dtype=torch.uint8, device=device)
+                self._mask_ws = torch.empty(lib.sanerf_mask_head_workspace_bytes(), dtype=torch.uint8, device=device)
             mw = [l.weight.detach().contiguous() for l in net]
-            a.mask_in_tiled = 1
+            a.mask_in_tiled = 2
         sam_full = self._alloc_rows_padded(N, self.samvit_mlp[0].dim_in, device) if want_sam else None
         base = {f: getattr(a, f) for f in ("rays_o", "rays_d", "image", "depth", "weights_sum", "cam_near_far", "bg_color",
                                            "inds0", "inds1", "weights2", "sigma2", "bins2", "f_image", "image_u8")}
@@ -415,8 +416,9 @@ class NeRFRenderer(nn.Module):
                 _lib.count_launch()
                 if tc_head:
                     out = logits[head:head + n]
-                    _lib.check(lib.sanerf_mask_mlp(_lib.ptr(mask_in), _lib.ptr(wts), _lib.ptr(mw[0]), _lib.ptr(mw[1]), _lib.ptr(mw[2]),
-                                                   n_inst, n, _lib.ptr(self._mask_ws), _lib.ptr(out), _lib.stream_ptr()), "sanerf_mask_mlp")
+                    _lib.check(lib.sanerf_mask_head(_lib.ptr(mask_in), _lib.ptr(wts), ctypes.byref(model.m_grid), _lib.ptr(mw[0]),
+                                                    _lib.ptr(mw[1]), _lib.ptr(mw[2]), n_inst, n, _lib.ptr(self._mask_ws), _lib.ptr(out),
+                                                    _lib.stream_ptr()), "sanerf_mask_head")
                     _lib.count_launch(2)
             if not tc_head:
                 point_masks = self.mask_mlp(mask_in[:n * 32 * width].view(n, 32, width))

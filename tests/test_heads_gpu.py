@@ -1,6 +1,9 @@
 """GPU: the tensor-core object head (`sanerf_mask_mlp`, csrc/heads.cu) through the C ABI vs a float64 evaluation of the
 reference's `mask_mlp` + compositing (nerf/renderer.py:376-385, nerf/network.py:31-66: bias-free SkipConnMLP
 143 -> 256 -> 256 -> n_inst, leaky_relu(0.01) between layers; logits = sum_samples w * point_masks)."""
+import ctypes
+
+import numpy as np
 import pytest
 import torch
 
@@ -11,7 +14,7 @@ DEV = "cuda"
 
 
 def _tile_transpose(x):
-    """[n_rays, 32, K] -> the [ceil(n_rays*32/128)][K][128] layout sanerf_render writes with mask_in_tiled=1."""
+    """[n_rays, 32, K] -> the [ceil(n_rays*32/128)][K][128] layout sanerf_render writes for the object head."""
     n, s, k = x.shape
     rows = x.reshape(n * s, k)
     pad = (-rows.shape[0]) % 128
@@ -20,32 +23,49 @@ def _tile_transpose(x):
     return rows.view(-1, 128, k).permute(0, 2, 1).contiguous()
 
 
-@pytest.mark.parametrize("n_rays,n_inst", [(1, 2), (3, 2), (4, 2), (5, 3), (640, 2), (4099, 16), (50000, 2)])
+@pytest.mark.parametrize("n_rays,n_inst", [(1, 2), (3, 2), (4, 2), (5, 3), (640, 2), (4099, 16), (20000, 2)])
 def test_mask_head_matches_fp64(n_rays, n_inst):
+    """records (point, geo_feat) -> in-kernel m_grid gather + mask_mlp + compositing, vs the C oracle's grid encoder
+    (bit-exact restatement of the reference kernel) followed by a float64 MLP."""
+    from oracle import kernels as K
+    from helpers import O
     from sanerf_hq_b200 import _lib
+    from sanerf_hq_b200.encoders import GridEncoder
+    from sanerf_hq_b200.renderer import NeRFRenderer
     lib = _lib.load()
     g = torch.Generator().manual_seed(n_rays * 31 + n_inst)
-    x = torch.rand(n_rays, 32, 143, generator=g) * 2 - 1
-    x[..., 128:] *= 3.0                                           # geo_feat channels: MLP outputs, larger range
+    enc = GridEncoder(num_levels=16, level_dim=8, log2_hashmap_size=19, desired_resolution=512).to(DEV)
+    emb = torch.rand(enc.embeddings.shape, generator=g) * 2 - 1
+    enc.embeddings.data.copy_(emb)
+    sp = O.grid_spec(16, 8, 16, 19, 512)
+    x01 = torch.rand(n_rays, 32, 3, generator=g)
+    x01[0, 0] = torch.tensor([1.25, 0.5, 0.5])                    # outside [0,1]^3 -> zero features
+    x01[0, 1] = torch.tensor([0.0, 1.0, 0.5])                     # on the boundary -> inside
+    geo = (torch.rand(n_rays, 32, 15, generator=g) * 2 - 1) * 3.0
     w = torch.rand(n_rays, 32, generator=g) ** 4
     w = w / w.sum(-1, keepdim=True).clamp(min=1e-6)
     bound = lambda fan_in: 1 / fan_in ** 0.5
     ws = [(torch.rand(256, 143, generator=g) * 2 - 1) * bound(143), (torch.rand(256, 256, generator=g) * 2 - 1) * bound(256),
           (torch.rand(n_inst, 256, generator=g) * 2 - 1) * bound(256)]
-    h = x.double()
+    B = n_rays * 32
+    feats = K.grid_encode_forward(x01.reshape(B, 3).contiguous(), emb, sp.offsets, B, 3, 8, 16, 16, np.log2(sp.per_level_scale), 16)
+    feats = feats.permute(1, 0, 2).reshape(n_rays, 32, 128)
+    h = torch.cat([feats, geo], dim=-1).double()
     for i, m in enumerate(ws):
         h = h @ m.double().t()
         if i < 2:
             h = torch.nn.functional.leaky_relu(h, 0.01)
     want = (w.double().unsqueeze(-1) * h).sum(-2)
 
-    xin = _tile_transpose(x).to(DEV)
+    rec = _tile_transpose(torch.cat([x01, geo], dim=-1)).to(DEV)
+    grid_t = _lib.GridT()
+    NeRFRenderer._fill_grid(grid_t, enc)
     wd = [m.to(DEV).contiguous() for m in ws]
     wts = w.to(DEV)
-    work = torch.empty(lib.sanerf_mask_mlp_workspace_bytes(), dtype=torch.uint8, device=DEV)
+    work = torch.empty(lib.sanerf_mask_head_workspace_bytes(), dtype=torch.uint8, device=DEV)
     out = torch.full((n_rays, n_inst), float("nan"), device=DEV)
-    _lib.check(lib.sanerf_mask_mlp(_lib.ptr(xin), _lib.ptr(wts), _lib.ptr(wd[0]), _lib.ptr(wd[1]), _lib.ptr(wd[2]), n_inst, n_rays,
-                                   _lib.ptr(work), _lib.ptr(out), _lib.stream_ptr()), "mask_mlp")
+    _lib.check(lib.sanerf_mask_head(_lib.ptr(rec), _lib.ptr(wts), ctypes.byref(grid_t), _lib.ptr(wd[0]), _lib.ptr(wd[1]), _lib.ptr(wd[2]),
+                                    n_inst, n_rays, _lib.ptr(work), _lib.ptr(out), _lib.stream_ptr()), "mask_head")
     torch.cuda.synchronize()
     got = out.cpu().double()
     assert torch.isfinite(got).all()
@@ -56,8 +76,9 @@ def test_mask_head_matches_fp64(n_rays, n_inst):
     # same result when the rays are processed with a different tiling (pointer shifted by one tile = 4 rays)
     if n_rays > 8:
         out2 = torch.empty(n_rays - 4, n_inst, device=DEV)
-        _lib.check(lib.sanerf_mask_mlp(xin[1:].contiguous().data_ptr(), wts[4:].contiguous().data_ptr(), _lib.ptr(wd[0]), _lib.ptr(wd[1]),
-                                       _lib.ptr(wd[2]), n_inst, n_rays - 4, _lib.ptr(work), _lib.ptr(out2), _lib.stream_ptr()), "mask_mlp")
+        _lib.check(lib.sanerf_mask_head(rec[1:].contiguous().data_ptr(), wts[4:].contiguous().data_ptr(), ctypes.byref(grid_t), _lib.ptr(wd[0]),
+                                        _lib.ptr(wd[1]), _lib.ptr(wd[2]), n_inst, n_rays - 4, _lib.ptr(work), _lib.ptr(out2),
+                                        _lib.stream_ptr()), "mask_head")
         assert torch.equal(out2, out[4:])
 
 
