@@ -91,7 +91,13 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_col, uin
 // the shared-memory input tile [143][128], from the 18-float records (point, geo_feat) the render kernel left per sample.
 // The gather (L1 / LSU bound) and the MLP (tensor / epilogue bound) therefore overlap on the same SM, and the 572-byte
 // per-sample input never exists in HBM.
-constexpr int kMaskThreads = 2 * kHeadThreads, kRecK = 18;
+#ifndef SANERF_MASK_PRODUCER_WARPS
+#define SANERF_MASK_PRODUCER_WARPS 16
+#endif
+constexpr int kProdWarps = SANERF_MASK_PRODUCER_WARPS;   // 8: two samples per lane quad and tile (31.5 ms / frame), 16: one (29.4 ms)
+static_assert(kProdWarps == 8 || kProdWarps == 16, "128 samples per tile = producer warps x 8 samples x passes");
+constexpr int kProdThreads = 32 * kProdWarps;
+constexpr int kMaskThreads = kHeadThreads + kProdThreads, kRecK = 18;
 
 __global__ void __launch_bounds__(kMaskThreads, 1)
     mask_head_kernel(const float* __restrict__ rec, const float* __restrict__ weights, const __grid_constant__ GridDev mg,
@@ -111,7 +117,7 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
         }
         tc::mbar_init(&bar_done, 1);
         tc::mbar_init(&bar_w2, 1);
-        tc::mbar_init(&bar_in_full, kHeadThreads);   // every producer thread arrives
+        tc::mbar_init(&bar_in_full, kProdThreads);   // every producer thread arrives
         tc::mbar_init(&bar_in_free, kHeadThreads);   // every consumer thread arrives
         tc::fence_mbar_init();
         tc::mbar_expect_tx(&bar_w2, kImg2 * 2);
@@ -197,7 +203,8 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
     if (producer) {
         // ---- producer warps: build the input tile of every tile of this CTA, one tile ahead of the tensor-core side --------
         const int pw = warp - 8, s8 = lane >> 2, qp = lane & 3, ptid = tid - kHeadThreads;
-        const int rowA = 8 * pw + s8, rowB = 64 + rowA;    // two samples per lane quad, gathered together (16 loads in flight)
+        constexpr bool kTwo = kProdWarps == 8;          // two samples per lane quad (16 loads in flight) or one
+        const int rowA = 8 * pw + s8, rowB = kTwo ? 64 + rowA : rowA;
         bool first = true;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const float* r = rec + (size_t)tile * kRecK * 128;
@@ -220,16 +227,18 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
             first = false;
 #pragma unroll 1
             for (int l = 0; l < 16; l++) {
-                float a0, a1, b0, b1;
+                float a0, a1, b0 = 0.f, b1 = 0.f;
                 quarter_level(mg, l, xa, qp, a0, a1);
-                quarter_level(mg, l, xb, qp, b0, b1);
+                if (kTwo) quarter_level(mg, l, xb, qp, b0, b1);
                 float* d0 = xin + (8 * l + 2 * qp) * 128;
                 d0[rowA] = ina ? a0 : 0.f;
                 d0[128 + rowA] = ina ? a1 : 0.f;
-                d0[rowB] = inb ? b0 : 0.f;
-                d0[128 + rowB] = inb ? b1 : 0.f;
+                if (kTwo) {
+                    d0[rowB] = inb ? b0 : 0.f;
+                    d0[128 + rowB] = inb ? b1 : 0.f;
+                }
             }
-            for (int i = ptid; i < 15 * 128; i += kHeadThreads) xin[128 * 128 + i] = __ldg(r + 3 * 128 + i);   // geo_feat rows
+            for (int i = ptid; i < 15 * 128; i += kProdThreads) xin[128 * 128 + i] = __ldg(r + 3 * 128 + i);   // geo_feat rows
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_in_full)) : "memory");
         }
     } else {
