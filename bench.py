@@ -335,7 +335,7 @@ def main():
                          "traffic": traffic, "peak_source": peak_src,
                          "kernel": "sanerf::render_kernel" if wl == "rgb" else
                                    ("sanerf::render_kernel + sanerf::samvit_mlp_kernel" if wl == "sam" else
-                                    "sanerf::render_kernel + sanerf::mask_mlp_kernel (5 chunks of 131072 rays)"),
+                                    "sanerf::render_kernel + sanerf::mask_head_kernel"),
                          "kernel_ms": k_ms, "algorithmic_bytes_per_ray": BYTES_PER_RAY[wl],
                          "mlp_tflops": FLOPS_PER_RAY[wl] * n_local / (k_ms * 1e-3) / 1e12},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * n_local * 12 * world,
