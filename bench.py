@@ -307,6 +307,18 @@ def main():
         e2e_ms = timed_loop(step_e2e, args.steps, args.warmup)[0] / args.steps
         e2e_value = n_total / (e2e_ms * 1e-3) / 1e6
 
+        # ---- informational: the same frame through render_image: host pose in (64 B), 8-bit image out ---------
+        cam_value = None
+        if wl == "rgb" and world == 1:
+            u8_host = torch.empty(n_local, 3, dtype=torch.uint8).pin_memory()
+
+            def step_cam(i):
+                out = model.render_image(poses[i % N_POSES], intr, H, W, return_uint8=True)
+                u8_host.copy_(out["image_u8"], non_blocking=True)
+
+            cam_ms = timed_loop(step_cam, args.steps, args.warmup)[0] / args.steps
+            cam_value = n_local / (cam_ms * 1e-3) / 1e6
+
     line = None
     if rank == 0:
         peaks = {}
@@ -339,7 +351,8 @@ def main():
                          "kernel_ms": k_ms, "algorithmic_bytes_per_ray": BYTES_PER_RAY[wl],
                          "mlp_tflops": FLOPS_PER_RAY[wl] * n_local / (k_ms * 1e-3) / 1e12},
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * n_local * 12 * world,
-                    "d2h_bytes_per_step": int(img_host.numel() * 4), "d2h": "rank 0 reads the gathered image"},
+                    "d2h_bytes_per_step": int(img_host.numel() * 4), "d2h": "rank 0 reads the gathered image",
+                    "render_image_uint8_value": cam_value},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
         }
