@@ -190,7 +190,7 @@ def main():
 
     import torch.distributed as dist
     from sanerf_hq_b200 import _lib
-    from sanerf_hq_b200.parallel import gather_rows
+    from sanerf_hq_b200.parallel import gather_dict
     from sanerf_hq_b200.rays import get_rays, lego_intrinsics, orbit_pose
 
     torch.cuda.set_device(local_rank)
@@ -225,7 +225,7 @@ def main():
         else:
             out = model.render(ro, rd, staged=True, perturb=False, image_width=TILE_HINT and W, **kw)
         if world > 1:
-            out = {k: gather_rows(out[k], [n_local] * world) for k in keys}
+            out = gather_dict({k: out[k] for k in keys}, [n_local] * world)   # one NCCL all-gather of the packed outputs
         return out
 
     flush = None if args.no_l2_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -6,6 +6,8 @@ No collective touches the data path before compositing: rays are independent (ev
 that every rank holds the whole frame, which is what the reference's (dead) eval-time
 `dist.all_gather(preds)` does (nerf/trainer.py:1582-1585).
 """
+import math
+
 import torch
 import torch.distributed as dist
 
@@ -38,6 +40,37 @@ def gather_rows(local, counts, group=None):
     return torch.cat([out[r * cmax: r * cmax + counts[r]] for r in range(world)], dim=0)
 
 
+def gather_dict(parts, counts, group=None):
+    """All-gather a dict of per-rank row blocks {key: [counts[rank], ...]} with ONE collective: the blocks are packed into one
+    flat fp32 buffer per rank ([image | depth | weights_sum | ...]), gathered once over NVLink, and unpacked into full-frame
+    tensors (rank-major row order, like `gather_rows`).  All tensors must be fp32; ragged counts are padded like `gather_rows`."""
+    world = dist.get_world_size(group)
+    if world == 1:
+        return dict(parts)
+    keys = sorted(parts)
+    cmax = max(counts)
+    widths = {k: math.prod(parts[k].shape[1:]) for k in keys}   # floats per row
+    per_rank = cmax * sum(widths.values())
+    ref = parts[keys[0]]
+    send = ref.new_zeros(per_rank)
+    off = 0
+    for k in keys:
+        n = parts[k].shape[0] * widths[k]
+        send[off:off + n] = parts[k].reshape(-1)
+        off += cmax * widths[k]
+    recv = ref.new_empty(per_rank * world)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.view(world, per_rank)
+    out, off = {}, 0
+    for k in keys:
+        w = widths[k]
+        block = recv[:, off:off + cmax * w].reshape(world, cmax, *parts[k].shape[1:])
+        out[k] = torch.cat([block[r, :counts[r]] for r in range(world)], dim=0) if any(c != cmax for c in counts) else \
+            block.reshape(world * cmax, *parts[k].shape[1:])
+        off += cmax * w
+    return out
+
+
 def render_sharded(render_fn, rays_o, rays_d, group=None, keys=("image", "depth", "weights_sum"), **kwargs):
     """Render all rays [N,3] cooperatively.  Every rank passes the same full ray set (or at least its own block
     in the right place); rank r renders rows shard_bounds(N, world, r) with `render_fn(rays_o, rays_d, **kwargs)
@@ -51,4 +84,4 @@ def render_sharded(render_fn, rays_o, rays_d, group=None, keys=("image", "depth"
     if world == 1:
         return {k: part[k] for k in keys if k in part}
     counts = [shard_bounds(N, world, r)[1] - shard_bounds(N, world, r)[0] for r in range(world)]
-    return {k: gather_rows(part[k], counts, group) for k in keys if k in part}
+    return gather_dict({k: part[k] for k in keys if k in part}, counts, group)   # ONE all-gather for all outputs

@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from sanerf_hq_b200.parallel import gather_rows, render_sharded, shard_bounds
+from sanerf_hq_b200.parallel import gather_dict, gather_rows, render_sharded, shard_bounds
 
 
 def _fake_render(rays_o, rays_d, **kw):
@@ -42,6 +42,8 @@ def _worker(rank, world, port, n, out_dir):
         counts = [shard_bounds(n, world, r)[1] - shard_bounds(n, world, r)[0] for r in range(world)]
         ok &= torch.equal(gather_rows(full["image"][lo:hi], counts), full["image"])
         ok &= torch.equal(gather_rows(full["depth"][lo:hi], counts), full["depth"])
+        packed = gather_dict({k: full[k][lo:hi] for k in ("image", "depth", "weights_sum")}, counts)   # one collective
+        ok &= all(torch.equal(packed[k], full[k]) for k in ("image", "depth", "weights_sum"))
         torch.save(bool(ok), os.path.join(out_dir, f"ok{rank}.pt"))
     finally:
         dist.destroy_process_group()
