@@ -47,9 +47,14 @@ def gather_dict(parts, counts, group=None):
     world = dist.get_world_size(group)
     if world == 1:
         return dict(parts)
-    keys = sorted(parts)
+    widths = {k: math.prod(parts[k].shape[1:]) for k in parts}   # floats per row
+    # wide tensors (the 256-d SAM features: 1 KB per ray) go out on their own, straight from the tensor the kernel wrote --
+    # packing them would cost two extra passes over hundreds of MB; the narrow per-ray outputs share one collective
+    wide = {k: gather_rows(parts[k], counts, group) for k in parts if widths[k] > 16}
+    keys = sorted(k for k in parts if k not in wide)
+    if not keys:
+        return wide
     cmax = max(counts)
-    widths = {k: math.prod(parts[k].shape[1:]) for k in keys}   # floats per row
     per_rank = cmax * sum(widths.values())
     ref = parts[keys[0]]
     send = ref.new_zeros(per_rank)
@@ -68,6 +73,7 @@ def gather_dict(parts, counts, group=None):
         out[k] = torch.cat([block[r, :counts[r]] for r in range(world)], dim=0) if any(c != cmax for c in counts) else \
             block.reshape(world * cmax, *parts[k].shape[1:])
         off += cmax * w
+    out.update(wide)
     return out
 
 
