@@ -5,7 +5,8 @@
 //     instance_mask_logits = sum_samples weights * point_masks             per ray
 // 6.57 MFLOP per ray, 4.2 TFLOP per 800x800 frame: the one dense contraction of the path.
 //
-// One CTA (8 warps) owns the tensor memory of its SM and walks over tiles of 128 samples (= 4 rays):
+// One CTA owns the tensor memory of its SM and walks over tiles of 128 samples (= 4 rays); 8 warps drive the tensor cores,
+// 16 producer warps gather the feature grid for the next tile (mask_head_kernel below):
 //   * activations live in TMEM as the A operand (bf16 hi | bf16 lo, two K values per 32-bit column), one row per TMEM lane;
 //     warps w and w+4 share the 32 lanes of sub-partition w and split the columns between them;
 //   * weights are pre-split into bf16 hi / lo operand images (K-major, no swizzle) by a prepare kernel and streamed from L2
@@ -16,8 +17,9 @@
 //   * split precision: D = Ah*Wh + Ah*Wl + Al*Wh (the dropped Al*Wl is 2^-18 relative), fp32 accumulation;
 //   * the last layer (N padded to 16) is composited with the sample weights by a warp reduction (one warp = one ray).
 //
-// Input layout: the render kernel writes the per-sample inputs "tile-transposed", [tile][k][128 rows], so that both its stores
-// and the loads here are coalesced (row r = ray*32 + sample; tile = r / 128).
+// Input layout: the render kernel writes one 18-float record (point in [0,1]^3, geo_feat) per sample "tile-transposed",
+// [tile][k][128 rows], so that both its stores and the loads here are coalesced (row r = ray*32 + sample; tile = r / 128); the
+// 143-wide MLP input [m_grid(x) (128) | geo_feat (15)] is assembled in shared memory by the producer warps.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -318,7 +320,7 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
 // leaky_relu(0.01) after all but the last, the 163-d input re-concatenated (hidden first) in front of layer 2
 // (weight [256, 256+163]), then nn.LayerNorm(256, eps=1e-5).  Runs once per RAY (0.69 MFLOP each).
 // Same machinery as the object head: 128 rays per tile, activations in TMEM (bf16 hi | lo), weight K-chunks streamed through
-// the cp.async ring.  Layer 2 is two accumulating phases: A = hidden (K=256), then A = the input tile again (K=163 -> 176).
+// the TMA-fed ring.  Layer 2 is two accumulating phases: A = hidden (K=256), then A = the input tile again (K=163 -> 176).
 // The input tile (row-major [128,163] fp32, 83 KB) is staged once in shared memory and used by both phases.
 // =====================================================================================================================
 constexpr int kSamIn = 163, kSamW = 256;   // (the input is padded to 176 = 11 k-steps of 16)
@@ -399,7 +401,7 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
         tc::tma_load_1d(stage_saddr + (g & 1) * kStageBytes, img + ch.img_off, bytes, &bar_full[g & 1]);
     };
     uint32_t g = 0;
-    // one accumulation phase of n_chunks chunks (see mask_mlp_kernel::run_chunks)
+    // one accumulation phase of n_chunks chunks (see mask_head_kernel::run_chunks)
     auto run_chunks = [&](int n_chunks) {
         tc::fence_before_sync();
         __syncthreads();

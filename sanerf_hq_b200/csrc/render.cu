@@ -235,7 +235,7 @@ struct Smem {
     // offsets in floats
     static constexpr int prop_w0 = 0;                        // [2 nets][hi, lo][16 x PKP operand image]
     static constexpr int prop_w1 = prop_w0 + 4 * 16 * PKP;   // [2][16]
-    // grid_mlp weights as tensor-core operand images (tc.cuh: K-major core matrices), tf32 hi part then lo part
+    // grid_mlp weights as tensor-core operand images (tc.cuh: K-major core matrices), bf16 hi image then bf16 lo image
     static constexpr int grid_w0 = (prop_w1 + 2 * 16 + 31) & ~31;  // 2 x [HG][GK]   (128-byte aligned)
     static constexpr int GKP = (GK + 15) & ~15;                    // first-layer K padded to the bf16 MMA step
     static constexpr int grid_w1 = grid_w0 + HG * GKP;             // all three layers: bf16 hi + lo images (2 x [N][K] bf16)
