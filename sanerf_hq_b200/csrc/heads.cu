@@ -5,15 +5,16 @@
 //     instance_mask_logits = sum_samples weights * point_masks             per ray
 // 6.57 MFLOP per ray, 4.2 TFLOP per 800x800 frame: the one dense contraction of the path.
 //
-// One CTA owns the tensor memory of its SM and walks over tiles of 128 samples (= 4 rays); 8 warps drive the tensor cores,
-// 16 producer warps gather the feature grid for the next tile (mask_head_kernel below):
+// One CTA owns the tensor memory of its SM and walks over tiles of 128 samples (= 4 rays); 8 warps run the epilogues, 16
+// producer warps gather the feature grid for the next tile, one thread issues the MMAs (mask_head_kernel below):
 //   * activations live in TMEM as the A operand (bf16 hi | bf16 lo, two K values per 32-bit column), one row per TMEM lane;
 //     warps w and w+4 share the 32 lanes of sub-partition w and split the columns between them;
 //   * weights are pre-split into bf16 hi / lo operand images (K-major, no swizzle) by a prepare kernel and streamed from L2
-//     through a double-buffered ring of K-chunks filled by TMA bulk copies (cp.async.bulk + mbarrier expect_tx; the whole
-//     MLP is 410 KB of operands -- it does not fit in shared memory); the MMA-issuing thread drives the ring;
-//   * D[128,256] fp32 accumulates in TMEM columns [256,512); the epilogue of a layer reads D, applies leaky_relu, splits to
-//     bf16 hi/lo and writes the next layer's A operand straight back to TMEM columns [0,256);
+//     through a four-stage ring of 32 KB K-chunks filled by TMA bulk copies (cp.async.bulk + mbarrier expect_tx; the whole
+//     MLP is 410 KB of operands -- it does not fit in shared memory);
+//   * D[128,256] fp32 accumulates in one 256-column TMEM region while A is read from the other; a layer is issued as two
+//     128-column halves, and the epilogue of a half (leaky_relu, bf16 hi/lo split) rewrites it IN PLACE as half of the next
+//     layer's A operand while the tensor cores work on the other half -- the two regions swap roles every layer;
 //   * split precision: D = Ah*Wh + Ah*Wl + Al*Wh (the dropped Al*Wl is 2^-18 relative), fp32 accumulation;
 //   * the last layer (N padded to 16) is composited with the sample weights by a warp reduction (one warp = one ray).
 //
@@ -21,6 +22,8 @@
 // [tile][k][128 rows], so that both its stores and the loads here are coalesced (row r = ray*32 + sample; tile = r / 128); the
 // 143-wide MLP input [m_grid(x) (128) | geo_feat (15)] is assembled in shared memory by the producer warps.
 #include <cuda_bf16.h>
+
+#include <cstdint>
 
 #include "common.cuh"
 #include "grid_dev.cuh"
@@ -37,6 +40,13 @@ constexpr int kChunksPerTile = kNCh0 + kNCh1;
 constexpr int kImg0 = 2 * kMaskH * kCh0, kImg1 = 2 * kMaskH * kCh1, kImg2 = 2 * kMaskNOut * kMaskH;
 constexpr int kOff1 = kNCh0 * kImg0, kOff2 = kOff1 + kNCh1 * kImg1, kImgTotal = kOff2 + kImg2;
 constexpr int kStageBytes = kImg1 * 2;  // 65536
+// object head: every layer is issued as two output halves of 128 columns; K chunks of 48 (layer 0) / 64 (layer 1)
+constexpr int kHalfN = 128, kKc0 = 48, kKc0N = 3, kKc1 = 64, kKc1N = 4;
+constexpr int kMaskChunks0 = 2 * kKc0N, kMaskChunks = kMaskChunks0 + 2 * kKc1N;   // 6 + 8 chunks per tile
+constexpr int kImgM0 = 2 * kHalfN * kKc0, kImgM1 = 2 * kHalfN * kKc1;             // bf16 elements (hi + lo image) per chunk
+constexpr int kOffM1 = kMaskChunks0 * kImgM0, kOffM2 = kOffM1 + 2 * kKc1N * kImgM1;
+static_assert(kOffM2 + kImg2 == kImgTotal, "same workspace size as one image per layer");
+constexpr int kMaskStages = 4, kMaskStageBytes = kImgM1 * 2;                      // 4 x 32 KB
 constexpr uint32_t kColsAlo = 128, kColsD = 256;
 
 using tc::idesc_bf16;
@@ -46,29 +56,32 @@ using tc::split_bf16;
 __host__ __device__ constexpr int img_index(int n, int k, int N) { return tc::bf16_img_index(n, k, N); }
 
 // ---- prepare: nn.Linear weights -> chunked operand images -------------------------------------------------------
+// Stream order of one tile (kMaskChunks chunks, each an [128 x KC] K-major image, bf16 hi followed by bf16 lo):
+//   layer 0: output half h = 0,1 x three 48-wide K chunks;  layer 1: output half h = 0,1 x four 64-wide K chunks;
+//   then the resident layer-2 image [16 x 256].
 __global__ void mask_prepare_kernel(const float* __restrict__ w0, const float* __restrict__ w1, const float* __restrict__ w2, uint32_t n_inst,
                                     __nv_bfloat16* __restrict__ img) {
     const int stride = gridDim.x * blockDim.x;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kMaskH * kMaskK0P; i += stride) {   // layer 0 [256,143(+1)]
-        const int n = i / kMaskK0P, k = i % kMaskK0P, c = k / kCh0, kk = k % kCh0;
+        const int n = i / kMaskK0P, k = i % kMaskK0P, c = (n / kHalfN) * kKc0N + k / kKc0, kk = k % kKc0, nn = n % kHalfN;
         __nv_bfloat16 h, l;
         split_bf16(k < kMaskK0 ? w0[n * kMaskK0 + k] : 0.f, h, l);
-        img[c * kImg0 + img_index(n, kk, kMaskH)] = h;
-        img[c * kImg0 + kMaskH * kCh0 + img_index(n, kk, kMaskH)] = l;
+        img[c * kImgM0 + img_index(nn, kk, kHalfN)] = h;
+        img[c * kImgM0 + kHalfN * kKc0 + img_index(nn, kk, kHalfN)] = l;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kMaskH * kMaskH; i += stride) {     // layer 1 [256,256]
-        const int n = i / kMaskH, k = i % kMaskH, c = k / kCh1, kk = k % kCh1;
+        const int n = i / kMaskH, k = i % kMaskH, c = (n / kHalfN) * kKc1N + k / kKc1, kk = k % kKc1, nn = n % kHalfN;
         __nv_bfloat16 h, l;
         split_bf16(w1[n * kMaskH + k], h, l);
-        img[kOff1 + c * kImg1 + img_index(n, kk, kMaskH)] = h;
-        img[kOff1 + c * kImg1 + kMaskH * kCh1 + img_index(n, kk, kMaskH)] = l;
+        img[kOffM1 + c * kImgM1 + img_index(nn, kk, kHalfN)] = h;
+        img[kOffM1 + c * kImgM1 + kHalfN * kKc1 + img_index(nn, kk, kHalfN)] = l;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kMaskNOut * kMaskH; i += stride) {  // layer 2 [n_inst,256] -> 16 rows
         const int n = i / kMaskH, k = i % kMaskH;
         __nv_bfloat16 h, l;
         split_bf16(n < (int)n_inst ? w2[n * kMaskH + k] : 0.f, h, l);
-        img[kOff2 + img_index(n, k, kMaskNOut)] = h;
-        img[kOff2 + kMaskNOut * kMaskH + img_index(n, k, kMaskNOut)] = l;
+        img[kOffM2 + img_index(n, k, kMaskNOut)] = h;
+        img[kOffM2 + kMaskNOut * kMaskH + img_index(n, k, kMaskNOut)] = l;
     }
 }
 
@@ -88,125 +101,157 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_col, uin
     }
 }
 
-// Warps 0..7 are the tensor-core side (as in samvit_mlp_kernel below); warps 8..15 are PRODUCERS: while the MMAs of tile i run
-// they gather m_grid (16 levels x 8 corners of 32-byte rows, quarter-row loads) for the 128 samples of tile i+1 straight into
-// the shared-memory input tile [143][128], from the 18-float records (point, geo_feat) the render kernel left per sample.
-// The gather (L1 / LSU bound) and the MLP (tensor / epilogue bound) therefore overlap on the same SM, and the 572-byte
-// per-sample input never exists in HBM.
+// The object head keeps the A operand INTERLEAVED: k-step j (16 k values) owns 16 columns, bf16 hi pairs in the first 8 and
+// bf16 lo pairs in the last 8 -- exactly the footprint of the 16 fp32 accumulator columns it is computed from, so that an
+// epilogue can convert D to the next layer's A in place.  STEPS k-steps of an [N x KC] image starting at img_saddr.
+template <int N, int STEPS>
+__device__ __forceinline__ void issue_ksteps(uint32_t d_tmem, uint32_t a_col, uint32_t img_saddr, uint32_t lo_off, uint32_t first_accumulate) {
+    constexpr uint32_t idesc = idesc_bf16(128, N);
+    constexpr uint32_t kstep_bytes = 2 * N * 16;
+#pragma unroll
+    for (int j = 0; j < STEPS; j++) {
+        const uint64_t bh = tc::smem_desc_kmajor(img_saddr + j * kstep_bytes, N * 16, 128);
+        const uint64_t bl = tc::smem_desc_kmajor(img_saddr + lo_off + j * kstep_bytes, N * 16, 128);
+        mma_bf16_ts(d_tmem, a_col + 16 * j, bh, idesc, (j > 0) ? 1u : first_accumulate);
+        mma_bf16_ts(d_tmem, a_col + 16 * j, bl, idesc, 1u);
+        mma_bf16_ts(d_tmem, a_col + 16 * j + 8, bh, idesc, 1u);
+    }
+}
+
+// Three roles in one CTA per SM (25 warps):
+//   * warps 0..7, the EPILOGUE side: warps w and w+4 share the 32 TMEM lanes of sub-partition w; "part" 0 (warps 0..3) owns
+//     output columns [0,128) of every layer, part 1 (warps 4..7) columns [128,256);
+//   * warps 8..23, the PRODUCERS: while the MLP of tile i runs they gather m_grid (16 levels x 8 corners of 32-byte rows,
+//     quarter-row loads) for the 128 samples of tile i+1 straight into the shared-memory input tile [143][128], from the
+//     18-float records (point, geo_feat) the render kernel left per sample -- the 572-byte per-sample input never exists in HBM;
+//   * warp 24, one thread: the ISSUER -- feeds the weight ring (TMA bulk copies, four 32 KB stages) and issues every tcgen05.mma.
+// Each layer is issued as two output halves.  As soon as half 0 of a layer has been committed, part 0 converts it (leaky_relu,
+// bf16 hi/lo split) IN PLACE to the first half of the next layer's A operand while the tensor cores are busy with half 1;
+// the next layer then starts on the K range that is ready while part 1 converts the second half.  The tensor pipe only waits
+// for an epilogue at the end of a tile.  TMEM: two 256-column regions that swap roles (A / D) from layer to layer.
 #ifndef SANERF_MASK_PRODUCER_WARPS
 #define SANERF_MASK_PRODUCER_WARPS 16
 #endif
-constexpr int kProdWarps = SANERF_MASK_PRODUCER_WARPS;   // 8: two samples per lane quad and tile (31.5 ms / frame), 16: one (29.4 ms)
+constexpr int kProdWarps = SANERF_MASK_PRODUCER_WARPS;   // 8: two samples per lane quad and tile, 16: one
 static_assert(kProdWarps == 8 || kProdWarps == 16, "128 samples per tile = producer warps x 8 samples x passes");
 constexpr int kProdThreads = 32 * kProdWarps;
-constexpr int kMaskThreads = kHeadThreads + kProdThreads, kRecK = 18;
+constexpr int kIssuerWarp = kHeadThreads / 32 + kProdWarps;
+constexpr int kMaskThreads = kHeadThreads + kProdThreads + 64, kRecK = 18;
 
 __global__ void __launch_bounds__(kMaskThreads, 1)
     mask_head_kernel(const float* __restrict__ rec, const float* __restrict__ weights, const __grid_constant__ GridDev mg,
                      const __nv_bfloat16* __restrict__ img, float* __restrict__ logits, uint32_t n_tiles, uint32_t n_rays, uint32_t n_inst) {
-    extern __shared__ __align__(128) uint8_t smem[];   // [2 stages x 64 KB][layer-2 image 16 KB][input tile 143 x 128 fp32]
-    __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done, bar_w2, bar_in_full, bar_in_free;
+    extern __shared__ __align__(128) uint8_t smem[];   // [4 stages x 32 KB][layer-2 image 16 KB][input tile 143 x 128 fp32]
+    __shared__ __align__(8) uint64_t bar_full[kMaskStages], bar_free[kMaskStages], bar_a[2], bar_d[2], bar_l2, bar_w2, bar_in_full[2], bar_in_free[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, part = (warp >> 2) & 1;
-    const bool producer = warp >= 8;
-    const uint32_t stage_saddr = tc::smem_u32(smem), w2_saddr = stage_saddr + 2 * kStageBytes;
+    const uint32_t stage_saddr = tc::smem_u32(smem), w2_saddr = stage_saddr + kMaskStages * kMaskStageBytes;
 
     // barriers + tensor memory; the resident layer-2 image arrives by TMA bulk copy
     if (tid == 0) {
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < kMaskStages; i++) {
             tc::mbar_init(&bar_full[i], 1);
             tc::mbar_init(&bar_free[i], 1);
         }
-        tc::mbar_init(&bar_done, 1);
+        for (int i = 0; i < 2; i++) {
+            tc::mbar_init(&bar_a[i], kHeadThreads / 2);   // the 128 threads of one part: "my half of the A operand is in TMEM"
+            tc::mbar_init(&bar_d[i], 1);                  // tcgen05.commit: "output half i of the layer is complete"
+        }
+        tc::mbar_init(&bar_l2, 1);
         tc::mbar_init(&bar_w2, 1);
-        tc::mbar_init(&bar_in_full, kProdThreads);   // every producer thread arrives
-        tc::mbar_init(&bar_in_free, kHeadThreads);   // every consumer thread arrives
+        for (int i = 0; i < 2; i++) {                    // the input tile is handed over in two halves: rows k < 64 | k >= 64
+            tc::mbar_init(&bar_in_full[i], kProdThreads);       // every producer thread arrives (+ the geo_feat bytes on half 1)
+            tc::mbar_init(&bar_in_free[i], kHeadThreads / 2);   // every thread of the part that reads the half arrives
+        }
         tc::fence_mbar_init();
         tc::mbar_expect_tx(&bar_w2, kImg2 * 2);
-        tc::tma_load_1d(w2_saddr, img + kOff2, kImg2 * 2, &bar_w2);
+        tc::tma_load_1d(w2_saddr, img + kOffM2, kImg2 * 2, &bar_w2);
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tm = tmem_base_s;
-    const uint32_t a_mma = tm, d_mma = tm + kColsD;
-    const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-    const uint32_t a_rw = a_mma + lane_base, d_rw = d_mma + lane_base;
-    uint32_t ph_full[2] = {0, 0}, ph_free[2] = {0, 0}, ph_done = 0;   // ph_full / ph_free are only used by thread 0
-
+    const uint32_t r0 = tm, r1 = tm + 256;   // the two regions
+    auto wait = [](uint64_t* bar, uint32_t parity) { tc::mbar_wait(bar, parity); };
     const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const uint32_t total_chunks = my_tiles * kChunksPerTile;
-    // Weight ring, driven entirely by thread 0 (which also issues the MMAs): chunk g of this CTA's stream lives in stage g & 1.
-    // TMA bulk copy -> bar_full[stage]; tcgen05.commit of the MMAs that read the stage -> bar_free[stage].
-    auto load_chunk = [&](uint32_t g) {   // thread 0 only
-        const uint32_t c = g % kChunksPerTile;
-        const void* src = c < kNCh0 ? img + c * kImg0 : img + kOff1 + (c - kNCh0) * kImg1;
-        const uint32_t bytes = (c < kNCh0 ? kImg0 : kImg1) * 2;
-        tc::mbar_expect_tx(&bar_full[g & 1], bytes);
-        tc::tma_load_1d(stage_saddr + (g & 1) * kStageBytes, src, bytes, &bar_full[g & 1]);
-    };
-    uint32_t g = 0;   // next chunk of the stream (meaningful in thread 0)
-    // One layer (or accumulation phase): everybody's A rows are in TMEM -> thread 0 walks the layer's chunks: wait for the
-    // bytes, issue the MMAs, commit, and refill the stage the previous chunk has released with the chunk after this one.
-    auto run_chunks = [&](int n_chunks, auto&& issue) {
-        tc::fence_before_sync();          // this thread's tcgen05.st / tcgen05.ld are ordered before the barrier
-        tc::named_barrier(1, kHeadThreads);   // the 8 tensor-core-side warps only
-        if (tid == 0) {
-            tc::fence_after_sync();
-            for (int c = 0; c < n_chunks; c++, g++) {
-                tc::mbar_wait(&bar_full[g & 1], ph_full[g & 1]);
-                ph_full[g & 1] ^= 1;
-                issue(c, stage_saddr + (g & 1) * kStageBytes);
-                tc::mma_commit(&bar_free[g & 1]);
-                if (c == n_chunks - 1) tc::mma_commit(&bar_done);
-                if (g + 1 < total_chunks) {
-                    if (g >= 1) {         // the MMAs of chunk g-1 read stage (g+1) & 1
-                        tc::mbar_wait(&bar_free[(g + 1) & 1], ph_free[(g + 1) & 1]);
-                        ph_free[(g + 1) & 1] ^= 1;
-                    }
-                    load_chunk(g + 1);
-                }
-            }
+    const uint32_t total_chunks = my_tiles * kMaskChunks;
+    auto load_chunk = [&](uint32_t g) {   // chunk g of this CTA's stream -> stage g % kMaskStages (whole warp calls, one lane issues)
+        const uint32_t c = g % kMaskChunks, s = g % kMaskStages;
+        const void* src = c < kMaskChunks0 ? img + c * kImgM0 : img + kOffM1 + (c - kMaskChunks0) * kImgM1;
+        const uint32_t bytes = (c < kMaskChunks0 ? kImgM0 : kImgM1) * 2;
+        if (tc::elect_one()) {
+            tc::mbar_expect_tx(&bar_full[s], bytes);
+            tc::tma_load_1d(stage_saddr + s * kMaskStageBytes, src, bytes, &bar_full[s]);
         }
         __syncwarp();
-        tc::mbar_wait(&bar_done, ph_done);
-        ph_done ^= 1;
-        tc::fence_after_sync();
     };
-    // D[:, part*128 .. +128) -> leaky_relu -> bf16 hi/lo -> A columns of the next layer
-    auto epilogue_to_a = [&] {
-        // two tcgen05.ld in flight per step: the TMEM read latency of one 16-column group hides behind the other's math
-#pragma unroll 1
-        for (int grp = 0; grp < 8; grp += 2) {
-            uint32_t t0[16], t1[16];
-            tc::tmem_ld16(d_rw + part * 128 + grp * 16, t0);
-            tc::tmem_ld16(d_rw + part * 128 + grp * 16 + 16, t1);
-            tc::tmem_ld_wait();
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-                float v[16];
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    const float x = __uint_as_float(h ? t1[i] : t0[i]);
-                    v[i] = x > 0.f ? x : 0.01f * x;   // F.leaky_relu default slope (network.py:66)
-                }
-                uint32_t hi[8], lo[8];
-                pack_split16(v, hi, lo);
-                tc::tmem_st8(a_rw + part * 64 + (grp + h) * 8, hi);
-                tc::tmem_st8(a_rw + kColsAlo + part * 64 + (grp + h) * 8, lo);
-            }
-        }
-        tc::tmem_st_wait();
-    };
+    float* xin = reinterpret_cast<float*>(smem + kMaskStages * kMaskStageBytes + kImg2 * 2);   // [143][128] input tile, filled by the producers
 
-    float* xin = reinterpret_cast<float*>(smem + 2 * kStageBytes + kImg2 * 2);   // [143][128] input tile, filled by the producers
-    uint32_t ph_in = 0;
-    if (producer) {
-        // ---- producer warps: build the input tile of every tile of this CTA, one tile ahead of the tensor-core side --------
-        const int pw = warp - 8, s8 = lane >> 2, qp = lane & 3, ptid = tid - kHeadThreads;
+    if (warp == kIssuerWarp) {
+        // ---- issuer: one warp owns the weight ring and the tensor pipe (warp-uniform control flow, one elected lane issues) ----
+        uint32_t ph_full = 0, ph_a = 0;   // one parity bit per barrier
+        auto wait_a = [&](int h) {
+            wait(&bar_a[h], (ph_a >> h) & 1);
+            ph_a ^= 1u << h;
+        };
+        uint32_t g = 0;
+        for (uint32_t t = 0; t < my_tiles; t++) {
+#pragma unroll 1
+            for (int c = 0; c < kMaskChunks; c++, g++) {
+                // layer 0 reads the whole input row; layer 1 starts on K half 0 and needs half 1 from its third chunk on
+                if (c == 0) {
+                    wait_a(0);
+                    wait_a(1);
+                } else if (c == kMaskChunks0) {
+                    wait_a(0);
+                } else if (c == kMaskChunks0 + kKc1N / 2) {
+                    wait_a(1);
+                }
+                const uint32_t s = g % kMaskStages, saddr = stage_saddr + s * kMaskStageBytes;
+                wait(&bar_full[s], (ph_full >> s) & 1);
+                ph_full ^= 1u << s;
+                tc::fence_after_sync();
+                if (tc::elect_one()) {
+                    if (c < kMaskChunks0) {          // layer 0: A = region 0, D = region 1
+                        const int h = c / kKc0N, kc = c % kKc0N;
+                        issue_ksteps<kHalfN, kKc0 / 16>(r1 + h * kHalfN, r0 + kc * kKc0, saddr, kHalfN * kKc0 * 2, kc > 0);
+                    } else {                         // layer 1: A = region 1, D = region 0
+                        const int cc = c - kMaskChunks0, h = cc / kKc1N, kc = cc % kKc1N;
+                        issue_ksteps<kHalfN, kKc1 / 16>(r0 + h * kHalfN, r1 + kc * kKc1, saddr, kHalfN * kKc1 * 2, kc > 0);
+                    }
+                    tc::mma_commit(&bar_free[s]);
+                    if (c == kKc0N - 1 || c == kMaskChunks0 + kKc1N - 1) tc::mma_commit(&bar_d[0]);
+                    if (c == kMaskChunks0 - 1 || c == kMaskChunks - 1) tc::mma_commit(&bar_d[1]);
+                }
+                __syncwarp();
+            }
+            // layer 2: 256 -> n_inst (16 output columns), resident image; A = region 0 (in place of D1), D = region 1
+            if (t == 0) wait(&bar_w2, 0);
+            wait_a(0);
+            tc::fence_after_sync();
+            if (tc::elect_one()) issue_ksteps<kMaskNOut, 8>(r1, r0, w2_saddr, kMaskNOut * kMaskH * 2, 0u);
+            __syncwarp();
+            wait_a(1);
+            tc::fence_after_sync();
+            if (tc::elect_one()) {
+                issue_ksteps<kMaskNOut, 8>(r1, r0 + 128, w2_saddr + 8 * 2 * kMaskNOut * 16, kMaskNOut * kMaskH * 2, 1u);
+                tc::mma_commit(&bar_l2);
+            }
+            __syncwarp();
+        }
+    } else if (warp == kIssuerWarp + 1) {
+        // ---- weight loader: keeps the ring full on its own, so that the issuer never waits for a stage to drain ---------
+        for (uint32_t g = 0; g < total_chunks; g++) {
+            if (g >= kMaskStages) wait(&bar_free[g % kMaskStages], ((g / kMaskStages) - 1) & 1);
+            load_chunk(g);
+        }
+    } else if (warp >= kHeadThreads / 32) {
+        // ---- producer warps: build the input tile of every tile of this CTA, one tile ahead of the tensor cores ----------
+        const int pw = warp - kHeadThreads / 32, s8 = lane >> 2, qp = lane & 3, ptid = tid - kHeadThreads;
         constexpr bool kTwo = kProdWarps == 8;          // two samples per lane quad (16 loads in flight) or one
         const int rowA = 8 * pw + s8, rowB = kTwo ? 64 + rowA : rowA;
+        uint32_t ph_in = 0;
         bool first = true;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const float* r = rec + (size_t)tile * kRecK * 128;
@@ -222,13 +267,20 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
                 ina &= !(xa[d] < 0.f || xa[d] > 1.f);
                 inb &= !(xb[d] < 0.f || xb[d] > 1.f);
             }
-            if (!first) {                  // the tensor-core side has copied the previous tile out of the buffer
-                tc::mbar_wait(&bar_in_free, ph_in);
-                ph_in ^= 1;
-            }
-            first = false;
+            if (!first) tc::mbar_wait(&bar_in_free[0], ph_in);   // part 0 has copied rows k < 64 of the previous tile out of the buffer
 #pragma unroll 1
             for (int l = 0; l < 16; l++) {
+                if (l == 8) {
+                    // levels 0..7 = rows k < 64 are complete: part 0 converts them while levels 8..15 are gathered
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_in_full[0])) : "memory");
+                    if (!first) tc::mbar_wait(&bar_in_free[1], ph_in);
+                    if (ptid == 0) {   // geo_feat rows [128,143): 7680 contiguous bytes on both sides, one TMA bulk copy
+                        asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(tc::smem_u32(&bar_in_full[1])),
+                                     "r"(15u * 128u * 4u)
+                                     : "memory");
+                        tc::tma_load_1d(tc::smem_u32(xin + 128 * 128), r + 3 * 128, 15 * 128 * 4, &bar_in_full[1]);
+                    }
+                }
                 float a0, a1, b0 = 0.f, b1 = 0.f;
                 quarter_level(mg, l, xa, qp, a0, a1);
                 if (kTwo) quarter_level(mg, l, xb, qp, b0, b1);
@@ -240,74 +292,96 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
                     d0[128 + rowB] = inb ? b1 : 0.f;
                 }
             }
-            for (int i = ptid; i < 15 * 128; i += kProdThreads) xin[128 * 128 + i] = __ldg(r + 3 * 128 + i);   // geo_feat rows
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_in_full)) : "memory");
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_in_full[1])) : "memory");
+            if (!first) ph_in ^= 1;
+            first = false;
         }
     } else {
-    // ---- tensor-core side -------------------------------------------------------------------------------------------
-    if (tid == 0 && total_chunks) load_chunk(0);
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        // ---- layer-0 input: this thread's row, k in [0,64) (part 0) or [64,144) (part 1) ---------------------------
-        tc::mbar_wait(&bar_in_full, ph_in);
-        ph_in ^= 1;
-        const float* src = xin + q * 32 + lane;
-        const int k_begin = part ? 64 : 0, n_grp = part ? 5 : 4;
-#pragma unroll 1
-        for (int grp = 0; grp < n_grp; grp++) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; i++) {
-                const int k = k_begin + grp * 16 + i;
-                v[i] = k < kMaskK0 ? src[k * 128] : 0.f;
-            }
-            uint32_t hi[8], lo[8];
-            pack_split16(v, hi, lo);
-            tc::tmem_st8(a_rw + (k_begin >> 1) + grp * 8, hi);
-            tc::tmem_st8(a_rw + kColsAlo + (k_begin >> 1) + grp * 8, lo);
-        }
-        tc::tmem_st_wait();
-        // ---- layer 0: 143(+1) -> 256 ------------------------------------------------------------------------------
-        run_chunks(kNCh0, [&](int c, uint32_t saddr) { issue_chunk<kMaskH, kCh0>(d_mma, a_mma + c * (kCh0 / 2), saddr, c > 0 ? 1u : 0u); });
-        // every tensor-core-side thread has passed the barrier inside run_chunks after reading its input row: hand the buffer
-        // back to the producers (who are already gathering... into it as soon as all 256 arrivals are in)
-        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_in_free)) : "memory");
-        epilogue_to_a();
-        // ---- layer 1: 256 -> 256 --------------------------------------------------------------------------------------
-        run_chunks(kNCh1, [&](int c, uint32_t saddr) { issue_chunk<kMaskH, kCh1>(d_mma, a_mma + c * (kCh1 / 2), saddr, c > 0 ? 1u : 0u); });
-        epilogue_to_a();
-        // ---- layer 2: 256 -> n_inst (16 output columns), resident image ----------------------------------------------
-        tc::fence_before_sync();
-        tc::named_barrier(1, kHeadThreads);
-        if (tid == 0) {
+        // ---- epilogue side ----------------------------------------------------------------------------------------------
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        uint32_t ph_in = 0, ph_d = 0, ph_l2 = 0;
+        auto arrive_a = [&] {              // my tcgen05.st have landed -> the issuer may read this half of the A operand
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_a[part])) : "memory");
+        };
+        // D[:, part*128 .. +128) of region `reg` -> leaky_relu -> bf16 hi/lo, written over the same 128 columns
+        auto epilogue_in_place = [&](uint32_t reg) {
+            wait(&bar_d[part], ph_d);
+            ph_d ^= 1;
             tc::fence_after_sync();
-            if (tile == blockIdx.x) tc::mbar_wait(&bar_w2, 0);   // first use: the resident image has landed
-            issue_chunk<kMaskNOut, kMaskH>(d_mma, a_mma, w2_saddr, 0u);
-            tc::mma_commit(&bar_done);
-        }
-        __syncwarp();
-        tc::mbar_wait(&bar_done, ph_done);
-        ph_done ^= 1;
-        tc::fence_after_sync();
-        // ---- composite: logits[ray] = sum_samples w * point_masks (renderer.py:384); one warp = one ray ---------------
-        if (part == 0) {
-            uint32_t t[16];
-            tc::tmem_ld16(d_rw, t);
-            tc::tmem_ld_wait();
-            const uint32_t ray = tile * 4 + q;
-            const float w = ray < n_rays ? __ldg(weights + (size_t)ray * 32 + lane) : 0.f;
+            const uint32_t base = reg + lane_base + part * kHalfN;
+            // two tcgen05.ld in flight per step: the TMEM read latency of one 16-column group hides behind the other's math
+#pragma unroll 1
+            for (int grp = 0; grp < 8; grp += 2) {
+                uint32_t t0[16], t1[16];
+                tc::tmem_ld16(base + grp * 16, t0);
+                tc::tmem_ld16(base + grp * 16 + 16, t1);
+                tc::tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < kMaskNOut; c++) {
-                if (c < (int)n_inst) {   // uniform
-                    float s = __fmul_rn(w, __uint_as_float(t[c]));
+                for (int h = 0; h < 2; h++) {
+                    float v[16];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-                    if (lane == 0 && ray < n_rays) logits[(size_t)ray * n_inst + c] = s;
+                    for (int i = 0; i < 16; i++) {
+                        const float x = __uint_as_float(h ? t1[i] : t0[i]);
+                        v[i] = x > 0.f ? x : 0.01f * x;   // F.leaky_relu default slope (network.py:66)
+                    }
+                    uint32_t hi[8], lo[8];
+                    pack_split16(v, hi, lo);
+                    tc::tmem_st8(base + (grp + h) * 16, hi);
+                    tc::tmem_st8(base + (grp + h) * 16 + 8, lo);
                 }
             }
+            arrive_a();
+        };
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // ---- layer-0 input: this thread's row, k in [0,64) (part 0) or [64,144) (part 1) -> region 0 ------------------
+            wait(&bar_in_full[part], ph_in);
+            ph_in ^= 1;
+            const float* src = xin + q * 32 + lane;
+            const int k_begin = part ? 64 : 0, n_grp = part ? 5 : 4;
+#pragma unroll 1
+            for (int grp = 0; grp < n_grp; grp++) {
+                float v[16];
+#pragma unroll
+                for (int i = 0; i < 16; i++) {
+                    const int k = k_begin + grp * 16 + i;
+                    v[i] = k < kMaskK0 ? src[k * 128] : 0.f;
+                }
+                uint32_t hi[8], lo[8];
+                pack_split16(v, hi, lo);
+                tc::tmem_st8(r0 + lane_base + k_begin + grp * 16, hi);
+                tc::tmem_st8(r0 + lane_base + k_begin + grp * 16 + 8, lo);
+            }
+            arrive_a();
+            // this thread has read its half of the input row: hand that half of the buffer back to the producers
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_in_free[part])) : "memory");
+            epilogue_in_place(r1);   // layer 0 (143 -> 256) -> A of layer 1
+            epilogue_in_place(r0);   // layer 1 (256 -> 256) -> A of layer 2
+            // ---- layer 2 done: nobody may touch region 0 (A of layer 2) or region 1 (D) before this ----------------------
+            wait(&bar_l2, ph_l2);
+            ph_l2 ^= 1;
+            tc::fence_after_sync();
+            // ---- composite: logits[ray] = sum_samples w * point_masks (renderer.py:384); one warp = one ray ---------------
+            if (part == 0) {
+                uint32_t t[16];
+                tc::tmem_ld16(r1 + lane_base, t);
+                tc::tmem_ld_wait();
+                const uint32_t ray = tile * 4 + q;
+                const float w = ray < n_rays ? __ldg(weights + (size_t)ray * 32 + lane) : 0.f;
+#pragma unroll
+                for (int c = 0; c < kMaskNOut; c++) {
+                    if (c < (int)n_inst) {   // uniform
+                        float s = __fmul_rn(w, __uint_as_float(t[c]));
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+                        if (lane == 0 && ray < n_rays) logits[(size_t)ray * n_inst + c] = s;
+                    }
+                }
+            }
+            // the arrivals on bar_a after the next input conversion order these TMEM reads before the MMAs that overwrite them
         }
-        // the next tile's first barrier (inside run_chunks) orders these TMEM reads before the next MMAs overwrite D
     }
-    }   // tensor-core side
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tm, 512);
@@ -600,7 +674,8 @@ int sanerf_mask_head(const float* records, const float* weights, const sanerf_gr
     cudaStream_t st = (cudaStream_t)stream;
     __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(workspace);
     mask_prepare_kernel<<<64, 256, 0, st>>>(w0, w1, w2, n_inst, img);
-    const size_t smem = 2 * (size_t)kStageBytes + (size_t)kImg2 * 2 + (size_t)kMaskK0 * 128 * sizeof(float);
+    const size_t smem = (size_t)kMaskStages * kMaskStageBytes + (size_t)kImg2 * 2 + (size_t)kMaskK0 * 128 * sizeof(float);
+    if (((uintptr_t)records & 15) != 0) return SANERF_E_CONFIG;   // the geo_feat rows of a tile travel by TMA bulk copy
     if (cudaFuncSetAttribute(mask_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return SANERF_E_SMEM;
@@ -609,8 +684,7 @@ int sanerf_mask_head(const float* records, const float* weights, const sanerf_gr
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t n_tiles = div_up(n_rays, 4u);
-    mask_head_kernel<<<n_tiles < (uint32_t)sms ? n_tiles : (uint32_t)sms, kMaskThreads, smem, st>>>(records, weights, mg, img, logits, n_tiles,
-                                                                                                    n_rays, n_inst);
+    mask_head_kernel<<<n_tiles < (uint32_t)sms ? n_tiles : (uint32_t)sms, kMaskThreads, smem, st>>>(records, weights, mg, img, logits, n_tiles, n_rays, n_inst);
     return check_launch();
 }
 

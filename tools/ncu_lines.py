@@ -2,11 +2,13 @@
 """Attribute ncu warp-stall samples to CUDA source lines.
 
     python tools/ncu_lines.py <report.ncu-rep> <cubin> <kernel-substring> [top]
+    (NCU_KERNEL=<regex> when the demangled name in the report differs from the mangled substring in the cubin)
 
 ncu's SASS page gives samples per instruction address; `nvdisasm -gi` gives the source line (incl. inlining) of every SASS
 offset of the same cubin (built with -lineinfo).  The first SASS row of the report is offset 0 of the kernel.
 """
 import csv
+import os
 import re
 import subprocess
 import sys
@@ -14,7 +16,8 @@ from collections import defaultdict
 
 rep, cubin, kname = sys.argv[1:4]
 top = int(sys.argv[4]) if len(sys.argv) > 4 else 40
-raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+raw = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + os.environ.get("NCU_KERNEL", kname)],
+                     capture_output=True, text=True).stdout   # reports with several kernels: keep the one asked for
 rows = list(csv.reader(raw.splitlines()))
 hdr = rows[1]
 ai, si, ni = hdr.index("Address"), hdr.index("Source"), hdr.index("# Samples")
