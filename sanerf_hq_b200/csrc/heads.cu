@@ -35,7 +35,6 @@ constexpr int kHeadThreads = 256;
 constexpr int kMaskK0 = 143, kMaskK0P = 144, kMaskH = 256, kMaskNOut = 16;
 constexpr int kCh0 = 48, kNCh0 = 3;   // layer 0: 144 = 3 chunks of 48
 constexpr int kCh1 = 64, kNCh1 = 4;   // layer 1: 256 = 4 chunks of 64
-constexpr int kChunksPerTile = kNCh0 + kNCh1;
 // operand-image sizes in bf16 elements (hi image followed by lo image)
 constexpr int kImg0 = 2 * kMaskH * kCh0, kImg1 = 2 * kMaskH * kCh1, kImg2 = 2 * kMaskNOut * kMaskH;
 constexpr int kOff1 = kNCh0 * kImg0, kOff2 = kOff1 + kNCh1 * kImg1, kImgTotal = kOff2 + kImg2;
@@ -47,6 +46,7 @@ constexpr int kImgM0 = 2 * kHalfN * kKc0, kImgM1 = 2 * kHalfN * kKc1;           
 constexpr int kOffM1 = kMaskChunks0 * kImgM0, kOffM2 = kOffM1 + 2 * kKc1N * kImgM1;
 static_assert(kOffM2 + kImg2 == kImgTotal, "same workspace size as one image per layer");
 constexpr int kMaskStages = 4, kMaskStageBytes = kImgM1 * 2;                      // 4 x 32 KB
+constexpr uint32_t kA0Col = 16;   // first TMEM column of the layer-0 input inside its region (the 16 before it hold the last layer's D)
 constexpr uint32_t kColsAlo = 128, kColsD = 256;
 
 using tc::idesc_bf16;
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
     mask_head_kernel(const float* __restrict__ rec, const float* __restrict__ weights, const __grid_constant__ GridDev mg,
                      const __nv_bfloat16* __restrict__ img, float* __restrict__ logits, uint32_t n_tiles, uint32_t n_rays, uint32_t n_inst) {
     extern __shared__ __align__(128) uint8_t smem[];   // [4 stages x 32 KB][layer-2 image 16 KB][input tile 143 x 128 fp32]
-    __shared__ __align__(8) uint64_t bar_full[kMaskStages], bar_free[kMaskStages], bar_a[2], bar_d[2], bar_l2, bar_w2, bar_in_full[2], bar_in_free[2];
+    __shared__ __align__(8) uint64_t bar_full[kMaskStages], bar_free[kMaskStages], bar_ain[2], bar_q[4], bar_d[2], bar_l2, bar_w2, bar_in_full[2], bar_in_free[2];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, q = warp & 3, part = (warp >> 2) & 1;
     const uint32_t stage_saddr = tc::smem_u32(smem), w2_saddr = stage_saddr + kMaskStages * kMaskStageBytes;
@@ -154,9 +154,11 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
             tc::mbar_init(&bar_free[i], 1);
         }
         for (int i = 0; i < 2; i++) {
-            tc::mbar_init(&bar_a[i], kHeadThreads / 2);   // the 128 threads of one part: "my half of the A operand is in TMEM"
-            tc::mbar_init(&bar_d[i], 1);                  // tcgen05.commit: "output half i of the layer is complete"
+            tc::mbar_init(&bar_ain[i], kHeadThreads / 2);   // the 128 threads of one part: "my half of the layer-0 input is in TMEM"
+            tc::mbar_init(&bar_d[i], 1);                    // tcgen05.commit: "output half i of the layer is complete"
         }
+        for (int i = 0; i < 4; i++) tc::mbar_init(&bar_q[i], kHeadThreads / 2);   // "columns [64 i, 64 i + 64) are the next layer's A"
+
         tc::mbar_init(&bar_l2, 1);
         tc::mbar_init(&bar_w2, 1);
         for (int i = 0; i < 2; i++) {                    // the input tile is handed over in two halves: rows k < 64 | k >= 64
@@ -190,35 +192,31 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
 
     if (warp == kIssuerWarp) {
         // ---- issuer: one warp owns the weight ring and the tensor pipe (warp-uniform control flow, one elected lane issues) ----
-        uint32_t ph_full = 0, ph_a = 0;   // one parity bit per barrier
-        auto wait_a = [&](int h) {
-            wait(&bar_a[h], (ph_a >> h) & 1);
-            ph_a ^= 1u << h;
+        uint32_t ph_full = 0, ph_ain = 0, ph_q = 0;   // one parity bit per barrier
+        auto wait_bit = [&](uint64_t* bars, uint32_t& ph, int i) {
+            wait(&bars[i], (ph >> i) & 1);
+            ph ^= 1u << i;
         };
         uint32_t g = 0;
         for (uint32_t t = 0; t < my_tiles; t++) {
+            const uint32_t X = (t & 1) ? r1 : r0, Y = (t & 1) ? r0 : r1;   // this tile: A0 in X, D0 -> Y, D1 -> X, D2 -> Y
 #pragma unroll 1
             for (int c = 0; c < kMaskChunks; c++, g++) {
-                // layer 0 reads the whole input row; layer 1 starts on K half 0 and needs half 1 from its third chunk on
-                if (c == 0) {
-                    wait_a(0);
-                    wait_a(1);
-                } else if (c == kMaskChunks0) {
-                    wait_a(0);
-                } else if (c == kMaskChunks0 + kKc1N / 2) {
-                    wait_a(1);
-                }
+                // layer 0, K chunk 0 reads input rows k < 48 (part 0's), the later chunks part 1's too;
+                // layer 1, K chunk kc of output half 0 is the first to read activation quarter kc
+                if (c < 2) wait_bit(bar_ain, ph_ain, c);
+                else if (c >= kMaskChunks0 && c < kMaskChunks0 + kKc1N) wait_bit(bar_q, ph_q, c - kMaskChunks0);
                 const uint32_t s = g % kMaskStages, saddr = stage_saddr + s * kMaskStageBytes;
                 wait(&bar_full[s], (ph_full >> s) & 1);
                 ph_full ^= 1u << s;
                 tc::fence_after_sync();
                 if (tc::elect_one()) {
-                    if (c < kMaskChunks0) {          // layer 0: A = region 0, D = region 1
+                    if (c < kMaskChunks0) {          // layer 0
                         const int h = c / kKc0N, kc = c % kKc0N;
-                        issue_ksteps<kHalfN, kKc0 / 16>(r1 + h * kHalfN, r0 + kc * kKc0, saddr, kHalfN * kKc0 * 2, kc > 0);
-                    } else {                         // layer 1: A = region 1, D = region 0
+                        issue_ksteps<kHalfN, kKc0 / 16>(Y + h * kHalfN, X + kA0Col + kc * kKc0, saddr, kHalfN * kKc0 * 2, kc > 0);
+                    } else {                         // layer 1
                         const int cc = c - kMaskChunks0, h = cc / kKc1N, kc = cc % kKc1N;
-                        issue_ksteps<kHalfN, kKc1 / 16>(r0 + h * kHalfN, r1 + kc * kKc1, saddr, kHalfN * kKc1 * 2, kc > 0);
+                        issue_ksteps<kHalfN, kKc1 / 16>(X + h * kHalfN, Y + kc * kKc1, saddr, kHalfN * kKc1 * 2, kc > 0);
                     }
                     tc::mma_commit(&bar_free[s]);
                     if (c == kKc0N - 1 || c == kMaskChunks0 + kKc1N - 1) tc::mma_commit(&bar_d[0]);
@@ -226,19 +224,18 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
                 }
                 __syncwarp();
             }
-            // layer 2: 256 -> n_inst (16 output columns), resident image; A = region 0 (in place of D1), D = region 1
+            // layer 2: 256 -> n_inst (16 output columns), resident image, one activation quarter (4 k-steps) at a time
             if (t == 0) wait(&bar_w2, 0);
-            wait_a(0);
-            tc::fence_after_sync();
-            if (tc::elect_one()) issue_ksteps<kMaskNOut, 8>(r1, r0, w2_saddr, kMaskNOut * kMaskH * 2, 0u);
-            __syncwarp();
-            wait_a(1);
-            tc::fence_after_sync();
-            if (tc::elect_one()) {
-                issue_ksteps<kMaskNOut, 8>(r1, r0 + 128, w2_saddr + 8 * 2 * kMaskNOut * 16, kMaskNOut * kMaskH * 2, 1u);
-                tc::mma_commit(&bar_l2);
+#pragma unroll 1
+            for (int qd = 0; qd < 4; qd++) {
+                wait_bit(bar_q, ph_q, qd);
+                tc::fence_after_sync();
+                if (tc::elect_one()) {
+                    issue_ksteps<kMaskNOut, 4>(Y, X + 64 * qd, w2_saddr + qd * 4 * (2 * kMaskNOut * 16), kMaskNOut * kMaskH * 2, qd > 0);
+                    if (qd == 3) tc::mma_commit(&bar_l2);
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     } else if (warp == kIssuerWarp + 1) {
         // ---- weight loader: keeps the ring full on its own, so that the issuer never waits for a stage to drain ---------
@@ -300,42 +297,8 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
         // ---- epilogue side ----------------------------------------------------------------------------------------------
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         uint32_t ph_in = 0, ph_d = 0, ph_l2 = 0;
-        auto arrive_a = [&] {              // my tcgen05.st have landed -> the issuer may read this half of the A operand
-            tc::tmem_st_wait();
-            tc::fence_before_sync();
-            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_a[part])) : "memory");
-        };
-        // D[:, part*128 .. +128) of region `reg` -> leaky_relu -> bf16 hi/lo, written over the same 128 columns
-        auto epilogue_in_place = [&](uint32_t reg) {
-            wait(&bar_d[part], ph_d);
-            ph_d ^= 1;
-            tc::fence_after_sync();
-            const uint32_t base = reg + lane_base + part * kHalfN;
-            // two tcgen05.ld in flight per step: the TMEM read latency of one 16-column group hides behind the other's math
-#pragma unroll 1
-            for (int grp = 0; grp < 8; grp += 2) {
-                uint32_t t0[16], t1[16];
-                tc::tmem_ld16(base + grp * 16, t0);
-                tc::tmem_ld16(base + grp * 16 + 16, t1);
-                tc::tmem_ld_wait();
-#pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    float v[16];
-#pragma unroll
-                    for (int i = 0; i < 16; i++) {
-                        const float x = __uint_as_float(h ? t1[i] : t0[i]);
-                        v[i] = x > 0.f ? x : 0.01f * x;   // F.leaky_relu default slope (network.py:66)
-                    }
-                    uint32_t hi[8], lo[8];
-                    pack_split16(v, hi, lo);
-                    tc::tmem_st8(base + (grp + h) * 16, hi);
-                    tc::tmem_st8(base + (grp + h) * 16 + 8, lo);
-                }
-            }
-            arrive_a();
-        };
-        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            // ---- layer-0 input: this thread's row, k in [0,64) (part 0) or [64,144) (part 1) -> region 0 ------------------
+        // layer-0 input of the next tile: this thread's row, k in [0,64) (part 0) or [64,144) (part 1), -> columns [16,160) of X
+        auto convert_input = [&](uint32_t X) {
             wait(&bar_in_full[part], ph_in);
             ph_in ^= 1;
             const float* src = xin + q * 32 + lane;
@@ -350,22 +313,64 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
                 }
                 uint32_t hi[8], lo[8];
                 pack_split16(v, hi, lo);
-                tc::tmem_st8(r0 + lane_base + k_begin + grp * 16, hi);
-                tc::tmem_st8(r0 + lane_base + k_begin + grp * 16 + 8, lo);
+                tc::tmem_st8(X + lane_base + kA0Col + k_begin + grp * 16, hi);
+                tc::tmem_st8(X + lane_base + kA0Col + k_begin + grp * 16 + 8, lo);
             }
-            arrive_a();
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_ain[part])) : "memory");
             // this thread has read its half of the input row: hand that half of the buffer back to the producers
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_in_free[part])) : "memory");
-            epilogue_in_place(r1);   // layer 0 (143 -> 256) -> A of layer 1
-            epilogue_in_place(r0);   // layer 1 (256 -> 256) -> A of layer 2
-            // ---- layer 2 done: nobody may touch region 0 (A of layer 2) or region 1 (D) before this ----------------------
+        };
+        // Output half h of a layer is complete in region `reg`: all eight warps convert it -- this warp the 64 columns
+        // [128 h + 64 part, +64) of its 32 rows -- leaky_relu -> bf16 hi/lo, written over the same columns (activation quarter 2h+part)
+        auto epilogue_in_place = [&](uint32_t reg, int h) {
+            wait(&bar_d[h], (ph_d >> h) & 1);
+            ph_d ^= 1u << h;
+            tc::fence_after_sync();
+            const uint32_t base = reg + lane_base + h * kHalfN + part * 64;
+            // two tcgen05.ld in flight per step: the TMEM read latency of one 16-column group hides behind the other's math
+#pragma unroll 1
+            for (int grp = 0; grp < 4; grp += 2) {
+                uint32_t t0[16], t1[16];
+                tc::tmem_ld16(base + grp * 16, t0);
+                tc::tmem_ld16(base + grp * 16 + 16, t1);
+                tc::tmem_ld_wait();
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    float v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; i++) {
+                        const float x = __uint_as_float(hh ? t1[i] : t0[i]);
+                        v[i] = x > 0.f ? x : 0.01f * x;   // F.leaky_relu default slope (network.py:66)
+                    }
+                    uint32_t hi[8], lo[8];
+                    pack_split16(v, hi, lo);
+                    tc::tmem_st8(base + (grp + hh) * 16, hi);
+                    tc::tmem_st8(base + (grp + hh) * 16 + 8, lo);
+                }
+            }
+            tc::tmem_st_wait();
+            tc::fence_before_sync();
+            asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_q[2 * h + part])) : "memory");
+        };
+        if (my_tiles) convert_input(r0);
+        uint32_t it = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, it++) {
+            const uint32_t X = (it & 1) ? r1 : r0, Y = (it & 1) ? r0 : r1;
+#pragma unroll 1
+            for (int e = 0; e < 4; e++) epilogue_in_place(e < 2 ? Y : X, e & 1);   // layer 0 (D in Y), then layer 1 (D in X)
+            // every layer-1 MMA has completed: Y (A of layer 1) is dead except for the 16 columns layer 2 writes -> stage the
+            // next tile's input there now, so that its layer 0 follows this tile's layer 2 without a gap
+            if (tile + gridDim.x < n_tiles) convert_input(Y);
+            if (part != 0) continue;
             wait(&bar_l2, ph_l2);
             ph_l2 ^= 1;
             tc::fence_after_sync();
             // ---- composite: logits[ray] = sum_samples w * point_masks (renderer.py:384); one warp = one ray ---------------
-            if (part == 0) {
+            {
                 uint32_t t[16];
-                tc::tmem_ld16(r1 + lane_base, t);
+                tc::tmem_ld16(Y + lane_base, t);
                 tc::tmem_ld_wait();
                 const uint32_t ray = tile * 4 + q;
                 const float w = ray < n_rays ? __ldg(weights + (size_t)ray * 32 + lane) : 0.f;
@@ -379,7 +384,7 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
                     }
                 }
             }
-            // the arrivals on bar_a after the next input conversion order these TMEM reads before the MMAs that overwrite them
+            // these columns are next written by layer 1 of the next tile, which waits for this warp's next epilogue (bar_q)
         }
     }
     tc::fence_before_sync();
