@@ -132,8 +132,8 @@ __device__ __forceinline__ void issue_ksteps(uint32_t d_tmem, uint32_t a_col, ui
 #ifndef SANERF_MASK_PRODUCER_WARPS
 #define SANERF_MASK_PRODUCER_WARPS 16
 #endif
-constexpr int kProdWarps = SANERF_MASK_PRODUCER_WARPS;   // 8: two samples per lane quad and tile, 16: one
-static_assert(kProdWarps == 8 || kProdWarps == 16, "128 samples per tile = producer warps x 8 samples x passes");
+constexpr int kProdWarps = SANERF_MASK_PRODUCER_WARPS;   // one sample per lane quad and tile (8 warps x two samples: 2 ms slower)
+static_assert(kProdWarps == 16, "128 samples per tile = producer warps x 8 samples");
 constexpr int kProdThreads = 32 * kProdWarps;
 constexpr int kIssuerWarp = kHeadThreads / 32 + kProdWarps;
 constexpr int kMaskThreads = kHeadThreads + kProdThreads + 64, kRecK = 18;
@@ -246,27 +246,20 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
     } else if (warp >= kHeadThreads / 32) {
         // ---- producer warps: build the input tile of every tile of this CTA, one tile ahead of the tensor cores ----------
         const int pw = warp - kHeadThreads / 32, s8 = lane >> 2, qp = lane & 3, ptid = tid - kHeadThreads;
-        constexpr bool kTwo = kProdWarps == 8;          // two samples per lane quad (16 loads in flight) or one
-        const int rowA = 8 * pw + s8, rowB = kTwo ? 64 + rowA : rowA;
+        const int rowA = 8 * pw + s8;
         uint32_t ph_in = 0;
         bool first = true;
         for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const float* r = rec + (size_t)tile * kRecK * 128;
-            float xa[3], xb[3];
+            float xa[3];
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-                xa[d] = __ldg(r + d * 128 + rowA);
-                xb[d] = __ldg(r + d * 128 + rowB);
-            }
-            bool ina = true, inb = true;   // points outside [0,1]^3 give zero features (gridencoder.cu:105-130)
+            for (int d = 0; d < 3; d++) xa[d] = __ldg(r + d * 128 + rowA);
+            bool ina = true;   // points outside [0,1]^3 give zero features (gridencoder.cu:105-130)
 #pragma unroll
-            for (int d = 0; d < 3; d++) {
-                ina &= !(xa[d] < 0.f || xa[d] > 1.f);
-                inb &= !(xb[d] < 0.f || xb[d] > 1.f);
-            }
+            for (int d = 0; d < 3; d++) ina &= !(xa[d] < 0.f || xa[d] > 1.f);
             if (!first) tc::mbar_wait(&bar_in_free[0], ph_in);   // part 0 has copied rows k < 64 of the previous tile out of the buffer
 #pragma unroll 1
-            for (int l = 0; l < 16; l++) {
+            for (int l = 0; l < 16; l += 2) {
                 if (l == 8) {
                     // levels 0..7 = rows k < 64 are complete: part 0 converts them while levels 8..15 are gathered
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_in_full[0])) : "memory");
@@ -278,16 +271,15 @@ __global__ void __launch_bounds__(kMaskThreads, 1)
                         tc::tma_load_1d(tc::smem_u32(xin + 128 * 128), r + 3 * 128, 15 * 128 * 4, &bar_in_full[1]);
                     }
                 }
-                float a0, a1, b0 = 0.f, b1 = 0.f;
+                // two levels per iteration: 16 independent loads in flight per lane
+                float a0, a1, b0, b1;
                 quarter_level(mg, l, xa, qp, a0, a1);
-                if (kTwo) quarter_level(mg, l, xb, qp, b0, b1);
+                quarter_level(mg, l + 1, xa, qp, b0, b1);
                 float* d0 = xin + (8 * l + 2 * qp) * 128;
                 d0[rowA] = ina ? a0 : 0.f;
                 d0[128 + rowA] = ina ? a1 : 0.f;
-                if (kTwo) {
-                    d0[rowB] = inb ? b0 : 0.f;
-                    d0[128 + rowB] = inb ? b1 : 0.f;
-                }
+                d0[8 * 128 + rowA] = ina ? b0 : 0.f;
+                d0[9 * 128 + rowA] = ina ? b1 : 0.f;
             }
             asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(tc::smem_u32(&bar_in_full[1])) : "memory");
             if (!first) ph_in ^= 1;
