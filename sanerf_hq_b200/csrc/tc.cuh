@@ -205,7 +205,8 @@ struct Group {
     uint64_t* bar;          // mbarrier the MMAs commit to
     uint32_t phase;         // parity of the next completion
     uint32_t bar_id;        // named barrier of the group (128 threads)
-    bool issuer;            // the one thread of the group that issues tcgen05.mma
+    bool issuer;            // the one thread of the group that takes / returns the TMEM slot
+    bool lead;              // warp 0 of the group: one elected lane of it issues tcgen05.mma
 };
 
 __device__ __forceinline__ Group make_group(uint32_t tmem_base, int group, int warp_in_group, int lane, uint64_t* bar) {
@@ -218,6 +219,7 @@ __device__ __forceinline__ Group make_group(uint32_t tmem_base, int group, int w
     g.phase = 0;
     g.bar_id = 1 + group;
     g.issuer = (warp_in_group == 0 && lane == 0);
+    g.lead = warp_in_group == 0;
     return g;
 }
 
@@ -278,10 +280,12 @@ __device__ __forceinline__ void group_round(Group& g, IssueFn&& issue) {
     tmem_st_wait();
     fence_before_sync();
     named_barrier(g.bar_id, 128);
-    if (g.issuer) {
-        fence_after_sync();
-        issue();
-        mma_commit(g.bar);
+    if (g.lead) {              // warp-uniform branch + elect: the MMAs are issued back to back from uniform registers
+        if (elect_one()) {
+            fence_after_sync();
+            issue();
+            mma_commit(g.bar);
+        }
     }
     __syncwarp();
     mbar_wait(g.bar, g.phase);
