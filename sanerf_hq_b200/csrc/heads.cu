@@ -460,12 +460,12 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
     const uint32_t tm = tmem_base_s, a_mma = tm, d_mma = tm + kColsD;
     const uint32_t lane_base = (uint32_t)(q * 32) << 16;
     const uint32_t a_rw = a_mma + lane_base, d_rw = d_mma + lane_base;
-    uint32_t ph_full[2] = {0, 0}, ph_free[2] = {0, 0}, ph_done = 0;   // ph_full / ph_free are only used by thread 0
+    uint32_t ph_full[2] = {0, 0}, ph_free[2] = {0, 0}, ph_done = 0;   // ph_full / ph_free are only used by warp 0
     const uint32_t my_tiles = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const uint32_t total_chunks = my_tiles * kSamChunks;
     const int row = q * 32 + lane;
 
-    auto load_chunk = [&](uint32_t g) {   // thread 0 only: TMA bulk copy of chunk g into stage g & 1
+    auto load_chunk = [&](uint32_t g) {   // one thread: TMA bulk copy of chunk g into stage g & 1
         const SamChunk ch = c_sam_chunks[g % kSamChunks];
         const uint32_t bytes = 2u * kSamW * ch.kc * 2u;
         tc::mbar_expect_tx(&bar_full[g & 1], bytes);
@@ -476,23 +476,28 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
     auto run_chunks = [&](int n_chunks) {
         tc::fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {   // warp-uniform ring bookkeeping; one elected lane issues the MMAs, commits and bulk copies
             tc::fence_after_sync();
             for (int c = 0; c < n_chunks; c++, g++) {
                 const SamChunk ch = c_sam_chunks[g % kSamChunks];
                 tc::mbar_wait(&bar_full[g & 1], ph_full[g & 1]);
                 ph_full[g & 1] ^= 1;
                 const uint32_t saddr = stage_saddr + (g & 1) * kStageBytes;
-                if (ch.kc == 64) issue_chunk_rt<64>(d_mma, a_mma + ch.a_col, saddr, ch.first ? 0u : 1u);
-                else issue_chunk_rt<48>(d_mma, a_mma + ch.a_col, saddr, ch.first ? 0u : 1u);
-                tc::mma_commit(&bar_free[g & 1]);
-                if (c == n_chunks - 1) tc::mma_commit(&bar_done);
+                if (tc::elect_one()) {
+                    tc::fence_after_sync();
+                    if (ch.kc == 64) issue_chunk_rt<64>(d_mma, a_mma + ch.a_col, saddr, ch.first ? 0u : 1u);
+                    else issue_chunk_rt<48>(d_mma, a_mma + ch.a_col, saddr, ch.first ? 0u : 1u);
+                    tc::mma_commit(&bar_free[g & 1]);
+                    if (c == n_chunks - 1) tc::mma_commit(&bar_done);
+                }
+                __syncwarp();
                 if (g + 1 < total_chunks) {
                     if (g >= 1) {
                         tc::mbar_wait(&bar_free[(g + 1) & 1], ph_free[(g + 1) & 1]);
                         ph_free[(g + 1) & 1] ^= 1;
                     }
-                    load_chunk(g + 1);
+                    if (tc::elect_one()) load_chunk(g + 1);
+                    __syncwarp();
                 }
             }
         }
