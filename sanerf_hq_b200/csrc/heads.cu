@@ -33,18 +33,14 @@ namespace sanerf {
 
 constexpr int kHeadThreads = 256;
 constexpr int kMaskK0 = 143, kMaskK0P = 144, kMaskH = 256, kMaskNOut = 16;
-constexpr int kCh0 = 48, kNCh0 = 3;   // layer 0: 144 = 3 chunks of 48
-constexpr int kCh1 = 64, kNCh1 = 4;   // layer 1: 256 = 4 chunks of 64
-// operand-image sizes in bf16 elements (hi image followed by lo image)
-constexpr int kImg0 = 2 * kMaskH * kCh0, kImg1 = 2 * kMaskH * kCh1, kImg2 = 2 * kMaskNOut * kMaskH;
-constexpr int kOff1 = kNCh0 * kImg0, kOff2 = kOff1 + kNCh1 * kImg1, kImgTotal = kOff2 + kImg2;
-constexpr int kStageBytes = kImg1 * 2;  // 65536
+constexpr int kStageBytes = 2 * kMaskH * 64 * 2;   // SAM head ring stage: a [256 x 64] chunk, bf16 hi + lo images = 65536 B
 // object head: every layer is issued as two output halves of 128 columns; K chunks of 48 (layer 0) / 64 (layer 1)
 constexpr int kHalfN = 128, kKc0 = 48, kKc0N = 3, kKc1 = 64, kKc1N = 4;
 constexpr int kMaskChunks0 = 2 * kKc0N, kMaskChunks = kMaskChunks0 + 2 * kKc1N;   // 6 + 8 chunks per tile
 constexpr int kImgM0 = 2 * kHalfN * kKc0, kImgM1 = 2 * kHalfN * kKc1;             // bf16 elements (hi + lo image) per chunk
-constexpr int kOffM1 = kMaskChunks0 * kImgM0, kOffM2 = kOffM1 + 2 * kKc1N * kImgM1;
-static_assert(kOffM2 + kImg2 == kImgTotal, "same workspace size as one image per layer");
+constexpr int kImg2 = 2 * kMaskNOut * kMaskH;                                     // resident layer-2 image
+constexpr int kOffM1 = kMaskChunks0 * kImgM0, kOffM2 = kOffM1 + 2 * kKc1N * kImgM1, kImgTotal = kOffM2 + kImg2;
+static_assert(kImgTotal == 2 * (kMaskH * kMaskK0P + kMaskH * kMaskH + kMaskNOut * kMaskH), "hi + lo image of every weight");
 constexpr int kMaskStages = 4, kMaskStageBytes = kImgM1 * 2;                      // 4 x 32 KB
 constexpr uint32_t kA0Col = 16;   // first TMEM column of the layer-0 input inside its region (the 16 before it hold the last layer's D)
 constexpr uint32_t kColsAlo = 128, kColsD = 256;
