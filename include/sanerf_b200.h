@@ -216,10 +216,11 @@ int sanerf_sample_pdf(const float *bins, const float *weights, const float *u, u
 /* Object (instance-mask) head on the tensor cores: replaces `m_grid(xyzs)`, `mask_mlp(cat[masks, geo_feat])` and the weighted
  * sum over samples (nerf/renderer.py:304-305, 376-385; SkipConnMLP 143 -> 256 -> 256 -> n_inst, no bias, leaky_relu 0.01,
  * network.py:119-123).  records: the per-sample (point, geo_feat) records written by sanerf_render with mask_in_tiled = 2,
- * [ceil(n_rays*32/128)][18][128], 16-byte aligned (SANERF_E_CONFIG otherwise: rows travel by TMA bulk copy); weights [n_rays,32] = the final-stage compositing weights; m_grid: the object feature grid
- * (HOST struct, 16 levels x 8 channels), gathered inside the kernel by producer warps while the MMAs run; w0 [256,143],
- * w1 [256,256], w2 [n_inst,256] in nn.Linear layout; workspace: device scratch of sanerf_mask_head_workspace_bytes() for the
- * split-precision operand images; logits [n_rays,n_inst].  bf16 hi/lo split operands, fp32 accumulation.  n_inst <= 16. */
+ * [ceil(n_rays*32/128)][18][128], 16-byte aligned (SANERF_E_CONFIG otherwise: rows travel by TMA bulk copy);
+ * weights [n_rays,32] = the final-stage compositing weights; m_grid: the object feature grid (HOST struct, 16 levels x 8
+ * channels), gathered inside the kernel by producer warps while the MMAs run; w0 [256,143], w1 [256,256], w2 [n_inst,256] in
+ * nn.Linear layout; workspace: device scratch of sanerf_mask_head_workspace_bytes() for the split-precision operand images;
+ * logits [n_rays,n_inst].  bf16 hi/lo split operands, fp32 accumulation.  n_inst <= 16. */
 size_t sanerf_mask_head_workspace_bytes(void);
 int sanerf_mask_head(const float *records, const float *weights, const sanerf_grid_t *m_grid, const float *w0, const float *w1,
                      const float *w2, uint32_t n_inst, uint32_t n_rays, void *workspace, float *logits, sanerf_stream_t stream);
