@@ -666,6 +666,7 @@ int sanerf_mask_head(const float* records, const float* weights, const sanerf_gr
     if (n_rays == 0) return 0;
     if (!records || !weights || !m_grid || !w0 || !w1 || !w2 || !workspace || !logits) return SANERF_E_NULL;
     if (n_inst == 0 || n_inst > (uint32_t)kMaskNOut || m_grid->num_levels != 16) return SANERF_E_CONFIG;
+    if (((uintptr_t)records & 15) != 0) return SANERF_E_CONFIG;   // the geo_feat rows of a tile travel by TMA bulk copy
     GridDev mg;
     int rc = fill_grid(mg, *m_grid, 8);
     if (rc) return rc;
@@ -673,7 +674,6 @@ int sanerf_mask_head(const float* records, const float* weights, const sanerf_gr
     __nv_bfloat16* img = reinterpret_cast<__nv_bfloat16*>(workspace);
     mask_prepare_kernel<<<64, 256, 0, st>>>(w0, w1, w2, n_inst, img);
     const size_t smem = (size_t)kMaskStages * kMaskStageBytes + (size_t)kImg2 * 2 + (size_t)kMaskK0 * 128 * sizeof(float);
-    if (((uintptr_t)records & 15) != 0) return SANERF_E_CONFIG;   // the geo_feat rows of a tile travel by TMA bulk copy
     if (cudaFuncSetAttribute(mask_head_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return SANERF_E_SMEM;

@@ -82,6 +82,39 @@ def test_mask_head_matches_fp64(n_rays, n_inst):
         assert torch.equal(out2, out[4:])
 
 
+def test_mask_head_rejects_bad_arguments():
+    """Argument validation of `sanerf_mask_head` (status codes instead of the reference's unchecked launches): misaligned records
+    (the geo_feat rows travel by TMA bulk copy: 16-byte alignment), more instances than the padded last layer, wrong grid."""
+    from sanerf_hq_b200 import _lib
+    from sanerf_hq_b200.encoders import GridEncoder
+    from sanerf_hq_b200.renderer import NeRFRenderer
+    lib = _lib.load()
+    enc = GridEncoder(num_levels=16, level_dim=8, log2_hashmap_size=19, desired_resolution=512).to(DEV)
+    grid_t = _lib.GridT()
+    NeRFRenderer._fill_grid(grid_t, enc)
+    rec = torch.zeros(2, 18, 128, device=DEV)
+    wts = torch.zeros(4, 32, device=DEV)
+    w0, w1, w2 = torch.zeros(256, 143, device=DEV), torch.zeros(256, 256, device=DEV), torch.zeros(2, 256, device=DEV)
+    work = torch.empty(lib.sanerf_mask_head_workspace_bytes(), dtype=torch.uint8, device=DEV)
+    out = torch.zeros(4, 2, device=DEV)
+
+    def call(rec_ptr, n_inst, grid):
+        return lib.sanerf_mask_head(ctypes.c_void_p(rec_ptr), _lib.ptr(wts), ctypes.byref(grid), _lib.ptr(w0), _lib.ptr(w1), _lib.ptr(w2),
+                                    n_inst, 4, _lib.ptr(work), _lib.ptr(out), _lib.stream_ptr())
+
+    assert call(rec.data_ptr(), 2, grid_t) == 0
+    assert call(rec.data_ptr() + 4, 2, grid_t) != 0                  # misaligned records
+    assert call(rec.data_ptr(), 17, grid_t) != 0                     # n_inst > 16
+    enc4 = GridEncoder(num_levels=16, level_dim=2, log2_hashmap_size=19, desired_resolution=512).to(DEV)
+    grid4 = _lib.GridT()
+    NeRFRenderer._fill_grid(grid4, enc4)
+    assert call(rec.data_ptr(), 2, grid4) != 0                       # the object grid has 8 channels per level
+    with pytest.raises(RuntimeError):
+        _lib.check(call(rec.data_ptr() + 4, 2, grid_t), "mask_head")
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+
+
 @pytest.mark.parametrize("n_rays", [1, 127, 128, 129, 4000, 70001])
 def test_samvit_head_matches_fp64(n_rays):
     """sanerf_samvit_mlp vs float64: five biased layers, skip concat (hidden first) before layer 2, leaky_relu, LayerNorm."""

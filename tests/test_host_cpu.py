@@ -177,3 +177,36 @@ def test_torch_helpers_match_oracle_on_cpu():
     n1, f1 = R.near_far_from_aabb(o, d, aabb, 0.2)
     n2, f2 = O.near_far_from_aabb(o, d, aabb, 0.2)
     assert torch.equal(n1, n2) and torch.equal(f1, f2)
+
+
+def test_head_entry_points_validate_arguments_before_any_launch():
+    """The C ABI returns a status instead of launching on bad arguments (the reference never checks): these paths return before
+    the first CUDA call, so they can be exercised without a GPU -- the dummy pointers are never dereferenced."""
+    from sanerf_hq_b200 import _lib
+    lib = _lib.load()
+    g = _lib.GridT()
+    g.embeddings = 0x1000
+    g.num_levels, g.level_dim = 16, 8
+    for l in range(17):
+        g.offset[l] = l * 524288
+    for l in range(16):
+        g.res[l] = 16 + l
+    P = ctypes.c_void_p
+
+    def mask_head(rec, n_inst, n_rays=4, w0=0x3000):
+        return lib.sanerf_mask_head(P(rec), P(0x2000), ctypes.byref(g), P(w0), P(0x4000), P(0x5000), n_inst, n_rays, P(0x6000), P(0x7000), None)
+
+    assert mask_head(0x10000, 2, n_rays=0) == 0          # empty batch: nothing to do
+    assert mask_head(0x10004, 2) != 0                    # records not 16-byte aligned (TMA bulk copies)
+    assert mask_head(0x10000, 0) != 0 and mask_head(0x10000, 17) != 0    # 1 <= n_inst <= 16
+    assert mask_head(0x10000, 2, w0=0) != 0              # null weight
+    g.level_dim = 2
+    assert mask_head(0x10000, 2) != 0                    # the object grid has 8 channels per level
+    g.level_dim, g.num_levels = 8, 12
+    assert mask_head(0x10000, 2) != 0                    # ... and 16 levels
+    assert lib.sanerf_error_string(mask_head(0x10004, 2))   # every status has a message
+    ws = (ctypes.c_void_p * 5)(*[0x1000] * 5)
+    assert lib.sanerf_samvit_mlp(P(0x1000), ws, ws, P(0x1000), P(0x1000), 0, P(0x1000), P(0x1000), None) == 0
+    assert lib.sanerf_samvit_mlp(None, ws, ws, P(0x1000), P(0x1000), 128, P(0x1000), P(0x1000), None) != 0
+    bad = (ctypes.c_void_p * 5)(0x1000, 0x1000, None, 0x1000, 0x1000)
+    assert lib.sanerf_samvit_mlp(P(0x1000), bad, ws, P(0x1000), P(0x1000), 128, P(0x1000), P(0x1000), None) != 0
