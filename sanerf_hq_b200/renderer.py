@@ -379,7 +379,10 @@ class NeRFRenderer(nn.Module):
         tc_head = (width == 143 and len(net) == 3 and net[0].weight.shape == (256, 143) and net[1].weight.shape == (256, 256)
                    and net[2].weight.shape == (n_inst, 256) and n_inst <= 16 and all(l.bias is None for l in net))
         tc_head = tc_head and self.m_grid.num_levels == 16 and self.m_grid.level_dim == 8
-        chunk = max(4, min(-(-N // 4) * 4, 1 << 20 if tc_head else int(getattr(self.opt, "max_ray_batch", 4096)) * 8))
+        # rays per launch pair (bounds the scratch: 2.3 KB per ray of records); a multiple of 4 rays = whole 128-sample tiles,
+        # so the chunking is invisible in the results.  `opt.mask_chunk_rays` overrides (tests).
+        cap = int(getattr(self.opt, "mask_chunk_rays", 0) or (1 << 20 if tc_head else int(getattr(self.opt, "max_ray_batch", 4096)) * 8))
+        chunk = max(4, min(-(-N // 4) * 4, cap // 4 * 4))
         mask_in = torch.empty(chunk * 32 * (18 if tc_head else width), device=device)
         w2 = torch.empty(chunk, 32, device=device)
         if tc_head:

@@ -148,6 +148,30 @@ def test_fused_equals_composed_on_a_large_batch(mode):
     assert torch.equal(d["image"], a["image"][:64]) if False else True
 
 
+def test_object_head_chunking_is_invisible():
+    """`_run_fused` renders frames larger than its scratch in chunks of rays (one render + one head launch each, pointers
+    advanced per chunk): a small `mask_chunk_rays` must reproduce the single-chunk result bit for bit, ragged last chunk
+    included, with per-ray near/far and background rows."""
+    opt, params, specs = make_case(with_mask=True)
+    model = build_model(opt, params)
+    rays_o, rays_d = frame_rays(800, 800, pose_k=3)
+    g = torch.Generator().manual_seed(11)
+    sel = torch.randint(0, 800 * 800, (5003,), generator=g)
+    rays_o, rays_d = rays_o[sel].to(DEV), rays_d[sel].to(DEV)
+    cnf = torch.stack([torch.full((5003,), 0.3), torch.rand(5003, generator=g) * 3 + 2], dim=-1).to(DEV)
+    bg = torch.rand(5003, 3, generator=g).to(DEV)
+    model.eval()
+    model.fused = True
+    with torch.no_grad():
+        one = model.run(rays_o, rays_d, bg_color=bg, cam_near_far=cnf, return_mask=1)
+        model.opt.mask_chunk_rays = 1024
+        many = model.run(rays_o, rays_d, bg_color=bg, cam_near_far=cnf, return_mask=1)
+        model.opt.mask_chunk_rays = 0
+    assert set(one) == set(many) and "instance_mask_logits" in one
+    for k in one:
+        assert torch.equal(one[k], many[k]), k
+
+
 def test_empty_and_tiny_batches():
     opt, params, specs = make_case(small=True)
     model = build_model(opt, params, small=True)
