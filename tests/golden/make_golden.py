@@ -19,9 +19,14 @@ Cases (weights from oracle.render_oracle.make_params, seeded; rays from the 8d o
   full_rgb   default-size network (L=16/T=2^19, 2x64 MLP), 96 rays of the 800x800 frame
   full_sam   default sizes + SAM head, 5x8 rays
   full_mask  default sizes + object head, 64 rays
+Option variants (small network; the option values travel inside the fixture as JSON):
+  opt_white  --background white (no opaque last sample, the frame is mixed with bg_color)
+  opt_box    contract=False, bound=1 (bounded scene: no contraction, aabb = [-1,1]^3)
+  opt_cnf    per-ray cam_near_far through the staged render loop (renderer.py:197-205 slices it per chunk)
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]
 """
+import json
 import os
 import sys
 import types
@@ -108,10 +113,11 @@ def param_digest(params):
 
 
 def make_case(name, small, with_sam=False, with_mask=False, H=32, W=32, rows=None, cols=None, batch=16, pose_k=3,
-              return_feats=0, return_mask=0, staged=True):
+              return_feats=0, return_mask=0, staged=True, optkw=None, per_ray_near_far=False):
     torch.manual_seed(0)
-    opt = O.default_opt(with_sam=with_sam, with_mask=with_mask, max_ray_batch=batch)
-    specs = O.default_specs(2, num_levels=4 if small else None)
+    optkw = dict(optkw or {})
+    opt = O.default_opt(with_sam=with_sam, with_mask=with_mask, max_ray_batch=batch, **optkw)
+    specs = O.default_specs(2 if opt.contract else opt.bound, num_levels=4 if small else None)
     params, specs = O.make_params(opt, specs, seed=7, hidden=16 if small else None)
     model = (SmallNetwork(opt) if small else ref_network.NeRFNetwork(opt)).eval()
     missing = model.load_state_dict(params, strict=True)
@@ -127,6 +133,11 @@ def make_case(name, small, with_sam=False, with_mask=False, H=32, W=32, rows=Non
     rec, restore = capture_searchsorted()
     with torch.no_grad():
         kw = dict(perturb=False, bg_color=1)
+        if per_ray_near_far:                  # a different [near, far] window per ray, some of them empty (near > far)
+            g = torch.Generator().manual_seed(5)
+            near = 0.2 + 2.5 * torch.rand(rays_o.shape[0], generator=g)
+            cnf = torch.stack([near, near + 4 * torch.rand(rays_o.shape[0], generator=g) - 0.3], dim=-1)
+            kw["cam_near_far"] = cnf
         if return_feats:
             kw.update(return_feats=1, H=h, W=w)
         if return_mask:
@@ -151,6 +162,10 @@ def make_case(name, small, with_sam=False, with_mask=False, H=32, W=32, rows=Non
     fix = dict(rays_o=rays_o.numpy(), rays_d=rays_d.numpy(), inds0=inds0.numpy().astype(np.int16),
                inds1=inds1.numpy().astype(np.int16), param_digest=np.float64(param_digest(params)),
                meta=np.array([int(small), int(with_sam), int(with_mask), h, w, batch, int(staged)], dtype=np.int32))
+    if optkw:
+        fix["optkw"] = np.array(json.dumps(optkw))
+    if per_ray_near_far:
+        fix["cam_near_far"] = kw["cam_near_far"].numpy()
     for k, v in out.items():
         if torch.is_tensor(v):
             fix["out_" + k] = v.numpy()
@@ -161,11 +176,17 @@ def make_case(name, small, with_sam=False, with_mask=False, H=32, W=32, rows=Non
 if __name__ == "__main__":
     torch.set_num_threads(8)
     print("reference:", ref_renderer.__file__)
-    make_case("cfg1_rgb", small=True)
-    make_case("cfg1_sam", small=True, with_sam=True, H=8, W=8, batch=64, return_feats=1, staged=False)
-    make_case("cfg1_mask", small=True, with_mask=True, H=16, W=16, batch=64, return_mask=1)
-    make_case("full_rgb", small=False, H=800, W=800, rows=(396, 404), cols=(394, 406), batch=4096)
-    make_case("full_sam", small=False, with_sam=True, H=800, W=800, rows=(300, 305), cols=(200, 208), batch=4096,
-              return_feats=1, staged=False)
-    make_case("full_mask", small=False, with_mask=True, H=800, W=800, rows=(100, 108), cols=(600, 608), batch=4096,
-              return_mask=1)
+    cases = {
+        "cfg1_rgb": dict(small=True),
+        "cfg1_sam": dict(small=True, with_sam=True, H=8, W=8, batch=64, return_feats=1, staged=False),
+        "cfg1_mask": dict(small=True, with_mask=True, H=16, W=16, batch=64, return_mask=1),
+        "full_rgb": dict(small=False, H=800, W=800, rows=(396, 404), cols=(394, 406), batch=4096),
+        "full_sam": dict(small=False, with_sam=True, H=800, W=800, rows=(300, 305), cols=(200, 208), batch=4096, return_feats=1,
+                         staged=False),
+        "full_mask": dict(small=False, with_mask=True, H=800, W=800, rows=(100, 108), cols=(600, 608), batch=4096, return_mask=1),
+        "opt_white": dict(small=True, H=16, W=16, batch=64, optkw=dict(background="white")),
+        "opt_box": dict(small=True, H=16, W=16, batch=64, optkw=dict(contract=False, bound=1)),
+        "opt_cnf": dict(small=True, H=16, W=16, batch=64, per_ray_near_far=True),
+    }
+    for name in (sys.argv[1:] or list(cases)):      # `python make_golden.py opt_white opt_box` regenerates only those
+        make_case(name, **cases[name])

@@ -50,7 +50,7 @@ def assert_close(cand, ref, tol=REL_TOL, what=""):
 def make_case(small=False, with_sam=False, with_mask=False, seed=7, table_scale=1.0, **optkw):
     """(opt, params, specs) exactly as tests/golden/make_golden.py builds them."""
     opt = O.default_opt(with_sam=with_sam, with_mask=with_mask, **optkw)
-    specs = O.default_specs(2, num_levels=4 if small else None)
+    specs = O.default_specs(2 if opt.contract else opt.bound, num_levels=4 if small else None)
     params, specs = O.make_params(opt, specs, seed=seed, hidden=16 if small else None, table_scale=table_scale)
     return opt, params, specs
 

@@ -1,5 +1,6 @@
 """CPU: the oracle (oracle/) reproduces the golden fixtures generated from the reference itself
 (tests/golden/make_golden.py).  This pins the oracle; the GPU tests then compare CUDA vs oracle."""
+import json
 import os
 
 import numpy as np
@@ -8,14 +9,17 @@ import torch
 
 from helpers import GOLDEN, O, make_case, param_digest, rel_err
 
-CASES = ["cfg1_rgb", "cfg1_sam", "cfg1_mask", "full_rgb", "full_sam", "full_mask"]
+CASES = ["cfg1_rgb", "cfg1_sam", "cfg1_mask", "full_rgb", "full_sam", "full_mask",
+         "opt_white", "opt_box", "opt_cnf"]      # option variants: --background white, contract=False / bound=1, per-ray near/far
 
 
 @pytest.mark.parametrize("name", CASES)
 def test_oracle_matches_reference_fixture(name):
     fx = np.load(os.path.join(GOLDEN, name + ".npz"))
     small, with_sam, with_mask, h, w, batch, staged = [int(v) for v in fx["meta"]]
-    opt, params, specs = make_case(small=bool(small), with_sam=bool(with_sam), with_mask=bool(with_mask), max_ray_batch=batch)
+    optkw = json.loads(str(fx["optkw"])) if "optkw" in fx.files else {}
+    cnf = torch.from_numpy(fx["cam_near_far"]) if "cam_near_far" in fx.files else None
+    opt, params, specs = make_case(small=bool(small), with_sam=bool(with_sam), with_mask=bool(with_mask), max_ray_batch=batch, **optkw)
     # the seeded weights must be the ones the fixture was generated with
     assert abs(param_digest(params) - float(fx["param_digest"])) <= 1e-6 * float(fx["param_digest"])
     rays_o, rays_d = torch.from_numpy(fx["rays_o"]), torch.from_numpy(fx["rays_d"])
@@ -28,7 +32,8 @@ def test_oracle_matches_reference_fixture(name):
     N = rays_o.shape[0]
     step = batch if staged else N
     for head in range(0, N, step):
-        r, ex = O.run(params, specs, opt, rays_o[head:head + step], rays_d[head:head + step], **kw)
+        r, ex = O.run(params, specs, opt, rays_o[head:head + step], rays_d[head:head + step],
+                      cam_near_far=None if cnf is None else cnf[head:head + step], **kw)
         inds0.append(ex["pdf"][0]["inds"])
         inds1.append(ex["pdf"][1]["inds"])
         for k, v in r.items():

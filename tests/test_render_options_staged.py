@@ -1,0 +1,41 @@
+"""STAGED GPU tests (marker `gpu_staged`, NOT part of `-m gpu`): the fused and the composed render against the option-variant
+fixtures generated from the reference (tests/golden/make_golden.py: --background white, contract=False / bound=1, per-ray
+cam_near_far through the staged loop).  The oracle is pinned on these fixtures by tests/test_oracle_golden.py (CPU, green);
+the CUDA side was written after the round's GPU budget was spent.  On a B200:
+
+    python -m pytest tests/test_render_options_staged.py -m gpu_staged -q
+
+and, once green, move the three names into CASES of tests/test_render_gpu.py (the body below is the same test)."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, REL_TOL, assert_close, build_model, make_case
+
+pytestmark = [pytest.mark.gpu_staged, pytest.mark.skipif(not torch.cuda.is_available(), reason="no CUDA device")]
+DEV = "cuda"
+
+
+@pytest.mark.parametrize("fused", [True, False], ids=["fused", "composed"])
+@pytest.mark.parametrize("name", ["opt_white", "opt_box", "opt_cnf"])
+def test_render_matches_reference_option_fixture(name, fused):
+    fx = np.load(os.path.join(GOLDEN, name + ".npz"))
+    small, with_sam, with_mask, h, w, batch, staged = [int(v) for v in fx["meta"]]
+    optkw = json.loads(str(fx["optkw"])) if "optkw" in fx.files else {}
+    opt, params, specs = make_case(small=bool(small), with_sam=bool(with_sam), with_mask=bool(with_mask), max_ray_batch=batch, **optkw)
+    model = build_model(opt, params, small=bool(small))
+    model.fused = fused
+    rays_o, rays_d = torch.from_numpy(fx["rays_o"]).to(DEV), torch.from_numpy(fx["rays_d"]).to(DEV)
+    kw = dict(perturb=False, bg_color=1)
+    if "cam_near_far" in fx.files:
+        kw["cam_near_far"] = torch.from_numpy(fx["cam_near_far"]).to(DEV)
+    with torch.no_grad():
+        out = model.render(rays_o, rays_d, staged=bool(staged), **kw)
+    want_keys = {k[4:] for k in fx.files if k.startswith("out_")}
+    assert {k for k, v in out.items() if torch.is_tensor(v)} == want_keys
+    for k in sorted(want_keys):
+        assert out[k].shape == fx["out_" + k].shape, k
+        assert_close(out[k], fx["out_" + k], REL_TOL, f"{name}/{k}")
