@@ -23,6 +23,11 @@ Option variants (small network; the option values travel inside the fixture as J
   opt_white  --background white (no opaque last sample, the frame is mixed with bg_color)
   opt_box    contract=False, bound=1 (bounded scene: no contraction, aabb = [-1,1]^3)
   opt_cnf    per-ray cam_near_far through the staged render loop (renderer.py:197-205 slices it per chunk)
+Training-only helpers (renderer.py:17-57):
+  losses     the reference's `proposal_loss` and `distort_loss` on seeded three-stage bins / weights.  `distort_loss` calls the
+             third-party `torch_efficient_distloss.eff_distloss` (requirements.txt:21, unpinned, not installed here): the fixture
+             uses the PUBLISHED DEFINITION of that loss instead -- sum_ij w_i w_j |m_i - m_j| + 1/3 sum_i w_i^2 delta_i, averaged
+             over rays -- evaluated in float64 by brute force, plugged into the reference's own `distort_loss`.
 
     python tests/golden/make_golden.py [case ...]
 """
@@ -173,6 +178,35 @@ def make_case(name, small, with_sam=False, with_mask=False, H=32, W=32, rows=Non
     print(f"  wrote {name}.npz  ({rays_o.shape[0]} rays; keys {[k for k in fix if k.startswith('out_')]})")
 
 
+def make_losses(name="losses"):
+    g = torch.Generator().manual_seed(3)
+    N = 48
+    all_bins, all_weights = [], []
+    for T in (128, 64, 32):
+        b = torch.sort(torch.rand(N, T + 1, generator=g), dim=-1).values
+        b[:, 0], b[:, -1] = 0, 1
+        w = torch.rand(N, T, generator=g) ** 4
+        w = w / w.sum(-1, keepdim=True) * torch.rand(N, 1, generator=g)       # sums below one, like compositing weights
+        all_bins.append(b)
+        all_weights.append(w)
+    all_weights[1][:3] = 0                                                     # empty rays
+
+    def distloss_definition(w, m, interval):                                   # O(T^2), float64
+        w, m, interval = w.double(), m.double(), interval.double()
+        bi = (w[..., :, None] * w[..., None, :] * (m[..., :, None] - m[..., None, :]).abs()).sum(dim=(-1, -2))
+        uni = (1 / 3) * (interval * w.pow(2)).sum(dim=-1)
+        return (bi + uni).mean().float()
+
+    ref_renderer.eff_distloss = distloss_definition
+    pl = ref_renderer.proposal_loss(all_bins, all_weights)
+    dl = ref_renderer.distort_loss(all_bins[-1], all_weights[-1])
+    fix = {f"bins{i}": b.numpy() for i, b in enumerate(all_bins)}
+    fix.update({f"weights{i}": w.numpy() for i, w in enumerate(all_weights)})
+    fix.update(proposal_loss=np.float32(pl), distort_loss=np.float32(dl))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **fix)
+    print(f"  wrote {name}.npz  proposal_loss {float(pl):.6e}  distort_loss {float(dl):.6e}")
+
+
 if __name__ == "__main__":
     torch.set_num_threads(8)
     print("reference:", ref_renderer.__file__)
@@ -188,5 +222,8 @@ if __name__ == "__main__":
         "opt_box": dict(small=True, H=16, W=16, batch=64, optkw=dict(contract=False, bound=1)),
         "opt_cnf": dict(small=True, H=16, W=16, batch=64, per_ray_near_far=True),
     }
-    for name in (sys.argv[1:] or list(cases)):      # `python make_golden.py opt_white opt_box` regenerates only those
-        make_case(name, **cases[name])
+    for name in (sys.argv[1:] or list(cases) + ["losses"]):      # `python make_golden.py opt_white opt_box` regenerates only those
+        if name == "losses":
+            make_losses()
+        else:
+            make_case(name, **cases[name])

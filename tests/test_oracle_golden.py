@@ -82,3 +82,23 @@ def test_oracle_grid_kernel_edge_cases():
     # partial levels: max_level < L leaves the rest untouched (zero-filled by the caller)
     out2 = K.grid_encode_forward(x, emb, sp.offsets, 5, 3, 2, 16, 3, S, 16)
     assert torch.equal(out2[:3], out[:3]) and torch.all(out2[3:] == 0)
+
+
+def test_training_losses_match_reference_fixture():
+    """renderer.py:17-57, training only: `proposal_loss` against the reference's own function (fixture from make_golden.py) and
+    `distort_loss` against the published definition of `torch_efficient_distloss.eff_distloss` (third party, unpinned in
+    requirements.txt:21, not installed): sum_ij w_i w_j |m_i - m_j| + 1/3 sum_i w_i^2 delta_i evaluated in float64.  Both helpers
+    are device-agnostic torch code, so they are checked here on the CPU; fp32 prefix sums vs float64 brute force: 1e-5."""
+    import sanerf_hq_b200.renderer as R
+    fx = np.load(os.path.join(GOLDEN, "losses.npz"))
+    bins = [torch.from_numpy(fx[f"bins{i}"]) for i in range(3)]
+    weights = [torch.from_numpy(fx[f"weights{i}"]) for i in range(3)]
+    pl = float(R.proposal_loss(bins, weights))
+    dl = float(R.distort_loss(bins[-1], weights[-1]))
+    assert abs(pl - float(fx["proposal_loss"])) <= 1e-6 * abs(float(fx["proposal_loss"]))
+    assert abs(dl - float(fx["distort_loss"])) <= 1e-5 * abs(float(fx["distort_loss"]))
+    # gradients flow to the proposal weights only (the last level is the detached target, renderer.py:50-51)
+    ws = [w.clone().requires_grad_(True) for w in weights]
+    R.proposal_loss(bins, ws).backward()
+    assert ws[0].grad is not None and ws[1].grad is not None and ws[2].grad is None
+    assert float(ws[0].grad.abs().sum()) > 0
