@@ -23,6 +23,9 @@ Option variants (small network; the option values travel inside the fixture as J
   opt_white  --background white (no opaque last sample, the frame is mixed with bg_color)
   opt_box    contract=False, bound=1 (bounded scene: no contraction, aabb = [-1,1]^3)
   opt_cnf    per-ray cam_near_far through the staged render loop (renderer.py:197-205 slices it per chunk)
+Pure-torch helpers (renderer.py:60-139):
+  helpers    `contract` / `uncontract` / `near_far_from_aabb` / `sample_pdf` on adversarial inputs (ties, zeros, axis-parallel
+             rays, empty and single-spike weight rows)
 Training-only helpers (renderer.py:17-57):
   losses     the reference's `proposal_loss` and `distort_loss` on seeded three-stage bins / weights.  `distort_loss` calls the
              third-party `torch_efficient_distloss.eff_distloss` (requirements.txt:21, unpinned, not installed here): the fixture
@@ -178,6 +181,41 @@ def make_case(name, small, with_sam=False, with_mask=False, H=32, W=32, rows=Non
     print(f"  wrote {name}.npz  ({rays_o.shape[0]} rays; keys {[k for k in fix if k.startswith('out_')]})")
 
 
+def make_helpers(name="helpers"):
+    """The reference's pure-torch helpers on adversarial inputs (renderer.py:60-139)."""
+    g = torch.Generator().manual_seed(9)
+    x = (torch.rand(400, 3, generator=g) - 0.5) * 40
+    x[:40] = (torch.rand(40, 3, generator=g) - 0.5) * 2                      # inside the unit cube: identity
+    x[40] = torch.tensor([1.0, -1.0, 0.5])                                    # on the boundary, tie in the max coordinate
+    x[41] = torch.tensor([3.0, 3.0, -3.0])                                    # three-way tie
+    x[42] = torch.tensor([0.0, 0.0, 0.0])
+    x[43] = torch.tensor([1e6, -2.0, 7.0])
+    z = ref_renderer.contract(x)
+    o = (torch.rand(300, 3, generator=g) - 0.5) * 6
+    d = torch.nn.functional.normalize(torch.randn(300, 3, generator=g), dim=-1)
+    d[:10, 0] = 0                                                             # axis-parallel: the +1e-15 guard
+    d[10:20] = torch.tensor([0.0, 0.0, 1.0])
+    o[20:40] *= 0.1                                                           # origins inside the box
+    aabb = torch.tensor([-1.0, -1.0, -1.0, 1.0, 1.0, 1.0])
+    near, far = ref_renderer.near_far_from_aabb(o, d, aabb, 0.2)
+    fix = dict(contract_in=x.numpy(), contract_out=z.numpy(), uncontract_out=ref_renderer.uncontract(z).numpy(),
+               rays_o=o.numpy(), rays_d=d.numpy(), aabb=aabb.numpy(), near=near.numpy(), far=far.numpy())
+    for T0, T in ((128, 65), (64, 33)):
+        N = 96
+        w = torch.rand(N, T0, generator=g) ** 6
+        w[:8] = 0                                                             # empty rays: uniform pdf
+        w[8:16, : T0 // 2] = 0
+        w[16, 5] = 1e30                                                       # one dominant sample
+        w[17] = 1e-12
+        edges = torch.sort(torch.rand(N, T0 + 1, generator=g), dim=-1).values
+        edges[:, 0], edges[:, -1] = 0, 1
+        edges[32:64] = torch.linspace(0, 1, T0 + 1)
+        fix[f"pdf{T0}_bins"], fix[f"pdf{T0}_weights"] = edges.numpy(), w.numpy()
+        fix[f"pdf{T0}_out"] = ref_renderer.sample_pdf(edges, w, T, perturb=False).numpy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **fix)
+    print(f"  wrote {name}.npz  ({len(fix)} arrays)")
+
+
 def make_losses(name="losses"):
     g = torch.Generator().manual_seed(3)
     N = 48
@@ -222,8 +260,10 @@ if __name__ == "__main__":
         "opt_box": dict(small=True, H=16, W=16, batch=64, optkw=dict(contract=False, bound=1)),
         "opt_cnf": dict(small=True, H=16, W=16, batch=64, per_ray_near_far=True),
     }
-    for name in (sys.argv[1:] or list(cases) + ["losses"]):      # `python make_golden.py opt_white opt_box` regenerates only those
+    for name in (sys.argv[1:] or list(cases) + ["losses", "helpers"]):      # `python make_golden.py opt_white opt_box` regenerates only those
         if name == "losses":
             make_losses()
+        elif name == "helpers":
+            make_helpers()
         else:
             make_case(name, **cases[name])

@@ -102,3 +102,23 @@ def test_training_losses_match_reference_fixture():
     R.proposal_loss(bins, ws).backward()
     assert ws[0].grad is not None and ws[1].grad is not None and ws[2].grad is None
     assert float(ws[0].grad.abs().sum()) > 0
+
+
+def test_torch_helpers_match_reference_fixture():
+    """`contract` / `uncontract` / `near_far_from_aabb` / `sample_pdf` (renderer.py:60-139) on adversarial inputs, oracle AND
+    the drop-in module's own copies against outputs of the reference's functions (tests/golden/helpers.npz)."""
+    import sanerf_hq_b200.renderer as R
+    fx = np.load(os.path.join(GOLDEN, "helpers.npz"))
+    t = lambda k: torch.from_numpy(fx[k])
+    same = lambda a, b: torch.allclose(a, b, rtol=1e-6, atol=0, equal_nan=True)
+    for mod in (O, R):
+        z = mod.contract(t("contract_in"))
+        assert same(z, t("contract_out")), mod.__name__
+        if hasattr(mod, "uncontract"):
+            assert same(mod.uncontract(z), t("uncontract_out")), mod.__name__
+        near, far = mod.near_far_from_aabb(t("rays_o"), t("rays_d"), t("aabb"), 0.2)
+        assert same(near, t("near")) and same(far, t("far")), mod.__name__
+        for T0, T in ((128, 65), (64, 33)):
+            out = mod.sample_pdf(t(f"pdf{T0}_bins"), t(f"pdf{T0}_weights"), T)
+            out = out[0] if isinstance(out, tuple) else out
+            assert same(out, t(f"pdf{T0}_out")), (mod.__name__, T0)

@@ -39,3 +39,22 @@ def test_render_matches_reference_option_fixture(name, fused):
     for k in sorted(want_keys):
         assert out[k].shape == fx["out_" + k].shape, k
         assert_close(out[k], fx["out_" + k], REL_TOL, f"{name}/{k}")
+
+
+def test_fused_handles_adversarial_rays_like_the_oracle():
+    """Axis-parallel directions (the +1e-15 guard of near_far_from_aabb), origins inside the box, rays that miss it: the rays of
+    tests/golden/helpers.npz (whose near/far the reference itself produced) through the fused kernel vs the oracle."""
+    from helpers import O
+    fx = np.load(os.path.join(GOLDEN, "helpers.npz"))
+    rays_o, rays_d = torch.from_numpy(fx["rays_o"]), torch.from_numpy(fx["rays_d"])
+    for optkw in ({}, dict(contract=False, bound=1)):
+        opt, params, specs = make_case(small=True, **optkw)
+        model = build_model(opt, params, small=True)
+        model.fused = True
+        ref, _ = O.run(params, specs, opt, rays_o, rays_d)
+        with torch.no_grad():
+            out = model.run(rays_o.to(DEV), rays_d.to(DEV))
+        for k, v in ref.items():
+            got, nan = out[k].cpu(), torch.isnan(v)       # rays that miss a bound=1 box: the reference's depth is 0 * 1e9-ish = NaN
+            assert torch.equal(torch.isnan(got), nan), f"{optkw}/{k}: NaN pattern differs from the reference's"
+            assert_close(got[~nan], v[~nan], REL_TOL, f"{optkw}/{k}")
