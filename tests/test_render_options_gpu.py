@@ -1,11 +1,6 @@
-"""STAGED GPU tests (marker `gpu_staged`, NOT part of `-m gpu`): the fused and the composed render against the option-variant
-fixtures generated from the reference (tests/golden/make_golden.py: --background white, contract=False / bound=1, per-ray
-cam_near_far through the staged loop).  The oracle is pinned on these fixtures by tests/test_oracle_golden.py (CPU, green);
-the CUDA side was written after the round's GPU budget was spent.  On a B200:
-
-    python -m pytest tests/test_render_options_staged.py -m gpu_staged -q
-
-and, once green, move the three names into CASES of tests/test_render_gpu.py (the body below is the same test)."""
+"""GPU: the fused and the composed render against the option-variant fixtures generated from the reference
+(tests/golden/make_golden.py: --background white, contract=False / bound=1, per-ray cam_near_far through the staged loop) and
+against the oracle on adversarial rays.  The oracle is pinned on the same fixtures by tests/test_oracle_golden.py (CPU)."""
 import json
 import os
 
@@ -15,7 +10,7 @@ import torch
 
 from helpers import GOLDEN, REL_TOL, assert_close, build_model, make_case
 
-pytestmark = [pytest.mark.gpu_staged, pytest.mark.skipif(not torch.cuda.is_available(), reason="no CUDA device")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
