@@ -19,7 +19,14 @@
  *     std::runtime_error / TORCH_CHECK (unsupported D or C, null pointer, bad dtype).
  *     `sanerf_error_string` explains any of them.  The Python layer turns non-zero into
  *     RuntimeError, matching the reference's pybind behaviour.
- *   - floating point is fp32 (the reference forces fp16 off, main.py:217).
+ *   - every tensor in the interface is fp32 (the reference forces fp16 off, main.py:217).  Arithmetic: the encoder operators
+ *     of Part 1 and all element-wise / sampling / compositing steps of Part 2 are plain fp32 in the reference's operation order
+ *     (grid forward bit-exact against the reference kernel).  The dense layers of Part 2 run on the 5th-gen tensor cores in
+ *     SPLIT precision with fp32 accumulation: proposal MLPs 3xTF32 (operands hi+lo, products hi*hi + hi*lo + lo*hi, relative
+ *     error 2^-22 -- they decide sample placement and the sample_pdf index buffers); grid_mlp, mask_mlp, samvit_mlp bf16 hi+lo
+ *     operands (16 significant bits, the lo*lo product dropped, relative error 2^-18 per product); view_mlp fp32 CUDA cores.
+ *     Tested against the reference's own fp32 GPU path at 1e-3 relative (tests/test_ref_gpu_frames.py; DESIGN.md section 5
+ *     lists the measured margins).
  */
 #ifndef SANERF_B200_H
 #define SANERF_B200_H
@@ -33,7 +40,7 @@ extern "C" {
 
 typedef void *sanerf_stream_t; /* cudaStream_t */
 
-#define SANERF_ABI_VERSION 1
+#define SANERF_ABI_VERSION 2
 
 #define SANERF_OK 0
 #define SANERF_E_NULL (-1)        /* required pointer is NULL */
@@ -122,6 +129,7 @@ int sanerf_freq_encode_backward(const float *grad, const float *outputs, uint32_
  * ---------------------------------------------------------------------------------------- */
 
 #define SANERF_MAX_LEVELS 16
+#define SANERF_MAX_PEERS 8
 
 /* One multiresolution hash grid (a reference GridEncoder, gridencoder/grid.py:102-146). */
 typedef struct {
@@ -199,14 +207,20 @@ typedef struct {
     uint32_t tile_w;
     /* optional 8-bit image (trainer.py:1140-1143 `(pred * 255).astype(np.uint8)`): [N,3] uint8 */
     uint8_t *image_u8;
+    /* optional multi-GPU fan-out (Part 3): image / depth / weights_sum of every ray are ALSO stored into n_peer_out further
+     * buffers -- the other ranks' frame buffers in NVLink peer memory, pointers to the row of ray 0 of this call -- so the
+     * kernel's final stores are the all-gather of the narrow outputs.  0 = off. */
+    uint32_t n_peer_out;
+    float *peer_image[SANERF_MAX_PEERS];
+    float *peer_depth[SANERF_MAX_PEERS];
+    float *peer_weights_sum[SANERF_MAX_PEERS];
+    /* optional cap on the number of persistent CTAs (0 = one per SM): leaves SMs free for a concurrent kernel */
+    uint32_t max_ctas;
 } sanerf_render_args_t;
 
 /* `model` and `args` are HOST structs (copied at launch); the pointers inside are device pointers.
  * One persistent launch renders all N rays.  Returns launch status. */
 int sanerf_render(const sanerf_model_t *model, const sanerf_render_args_t *args, sanerf_stream_t stream);
-
-/* Number of kernels sanerf_render launches for this model/args combination (for launch accounting). */
-int sanerf_render_launch_count(const sanerf_model_t *model, const sanerf_render_args_t *args);
 
 /* Standalone sample_pdf (renderer.py:84-119), perturb=False: bins [N,T0+1], weights [N,T0] ->
  * new_bins [N,T], inds [N,T] (int16) ; T0+1 <= 129, T in {65,33} with u = the linspace table. */
@@ -239,6 +253,31 @@ int sanerf_samvit_mlp(const float *sam_in, const float *const *w, const float *c
  * Supported (K,H): (32,64) default network, (8,16) config #1, (16,32). */
 int sanerf_mlp3_tc(const float *x, const float *w0, const float *w1, const float *w2, float *out, uint32_t M, uint32_t K,
                    uint32_t H, sanerf_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Part 3 -- frame buffers in NVLink peer memory (multi-GPU: row-sharded rendering)
+ *
+ * Replaces the reference's (dead) eval-time `dist.all_gather(preds)` (nerf/trainer.py:1582-1601): one process per GPU, every
+ * rank owns a full-frame buffer that the other ranks map over NVLink (CUDA IPC) and write their row block into -- from the
+ * render kernel itself (sanerf_render_args_t::peer_*) or by copy-engine pushes -- followed by one flag barrier.  These are the
+ * only entry points that allocate (the buffers must be IPC-exportable cudaMalloc allocations) and the host side of
+ * sanerf_peer_alloc / free / open / close synchronises like cudaMalloc does; push and barrier are asynchronous.
+ * ---------------------------------------------------------------------------------------- */
+#define SANERF_PEER_HANDLE_BYTES 64
+
+int sanerf_peer_alloc(size_t bytes, void **ptr);                                   /* zero-filled device buffer */
+int sanerf_peer_free(void *ptr);
+int sanerf_peer_export(const void *ptr, uint8_t handle[SANERF_PEER_HANDLE_BYTES]); /* handle to send to the other processes */
+int sanerf_peer_open(const uint8_t handle[SANERF_PEER_HANDLE_BYTES], void **ptr);  /* map a peer's buffer (lazy peer access) */
+int sanerf_peer_close(void *ptr);
+/* n_dst asynchronous device-to-device copies of `bytes` from src to dst[i] on streams[i] (HOST arrays): copy engines, no SMs */
+int sanerf_peer_push(void *const *dst, const void *src, size_t bytes, uint32_t n_dst, const sanerf_stream_t *streams);
+/* flags: HOST array of `world` device pointers, flags[r] = rank r's flag array (SANERF_MAX_PEERS uint32, zero-initialised) as
+ * mapped in this process.  Enqueues on `stream`: signal every peer with `epoch` (strictly increasing from 1), wait until every
+ * peer has signalled >= epoch.  After it, everything the peers enqueued before THEIR barrier of the same epoch on the stream
+ * they passed is visible here.  status: optional device word set to 1 if a peer did not arrive within timeout_s seconds. */
+int sanerf_peer_barrier(uint32_t *const *flags, uint32_t rank, uint32_t world, uint32_t epoch, float timeout_s, uint32_t *status,
+                        sanerf_stream_t stream);
 
 #ifdef __cplusplus
 }

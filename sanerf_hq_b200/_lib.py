@@ -12,6 +12,8 @@ from . import build as _build
 
 _u32, _f32, _vp, _i32 = ctypes.c_uint32, ctypes.c_float, ctypes.c_void_p, ctypes.c_int
 MAX_LEVELS = 16
+MAX_PEERS = 8
+PEER_HANDLE_BYTES = 64
 
 
 class GridT(ctypes.Structure):
@@ -34,7 +36,9 @@ class RenderArgsT(ctypes.Structure):
                 ("bg_color", _vp), ("bg_rows", _u32), ("bg_scalar", _f32),
                 ("image", _vp), ("depth", _vp), ("weights_sum", _vp), ("sam_in", _vp), ("mask_in", _vp),
                 ("mask_in_tiled", _u32), ("inds0", _vp), ("inds1", _vp), ("weights2", _vp), ("sigma2", _vp), ("bins2", _vp), ("f_image", _vp),
-                ("cam_w", _u32), ("cam_ray0", _u32), ("cam_intrinsics", _f32 * 4), ("cam_pose", _f32 * 12), ("tile_w", _u32), ("image_u8", _vp)]
+                ("cam_w", _u32), ("cam_ray0", _u32), ("cam_intrinsics", _f32 * 4), ("cam_pose", _f32 * 12), ("tile_w", _u32), ("image_u8", _vp),
+                ("n_peer_out", _u32), ("peer_image", _vp * MAX_PEERS), ("peer_depth", _vp * MAX_PEERS), ("peer_weights_sum", _vp * MAX_PEERS),
+                ("max_ctas", _u32)]
 
 
 # name -> argtypes (restype is int for all but the two noted)
@@ -51,18 +55,22 @@ PROTOTYPES = {
     "sanerf_freq_encode_forward": [_vp, _u32, _u32, _u32, _u32, _vp, _vp],
     "sanerf_freq_encode_backward": [_vp, _vp, _u32, _u32, _u32, _u32, _vp, _vp],
     "sanerf_render": [ctypes.POINTER(ModelT), ctypes.POINTER(RenderArgsT), _vp],
-    "sanerf_render_launch_count": [ctypes.POINTER(ModelT), ctypes.POINTER(RenderArgsT)],
     "sanerf_sample_pdf": [_vp, _vp, _vp, _u32, _u32, _u32, _vp, _vp, _vp],
     "sanerf_mlp3_tc": [_vp, _vp, _vp, _vp, _vp, _u32, _u32, _u32, _vp],
     "sanerf_mask_head_workspace_bytes": [],
     "sanerf_mask_head": [_vp, _vp, ctypes.POINTER(GridT), _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp],
     "sanerf_samvit_mlp_workspace_bytes": [],
     "sanerf_samvit_mlp": [_vp, _vp * 5, _vp * 5, _vp, _vp, _u32, _vp, _vp, _vp],
+    "sanerf_peer_alloc": [ctypes.c_size_t, ctypes.POINTER(_vp)],
+    "sanerf_peer_free": [_vp],
+    "sanerf_peer_export": [_vp, ctypes.c_char_p],
+    "sanerf_peer_open": [ctypes.c_char_p, ctypes.POINTER(_vp)],
+    "sanerf_peer_close": [_vp],
+    "sanerf_peer_push": [ctypes.POINTER(_vp), _vp, ctypes.c_size_t, _u32, ctypes.POINTER(_vp)],
+    "sanerf_peer_barrier": [ctypes.POINTER(_vp), _u32, _u32, _u32, _f32, _vp, _vp],
     "sanerf_abi_version": [],
     "sanerf_error_string": [_i32],
 }
-OPTIONAL = set()
-
 _lib = None
 
 
@@ -85,8 +93,6 @@ def load():
     L = ctypes.CDLL(path)
     for name, argtypes in PROTOTYPES.items():
         if not hasattr(L, name):
-            if name in OPTIONAL:
-                continue
             raise RuntimeError(f"{path} does not export {name}; rebuild the library")
         fn = getattr(L, name)
         fn.argtypes = argtypes
@@ -123,6 +129,28 @@ def require_cuda(*tensors, what="sanerf_hq_b200"):
 
 
 launch_counter = {"n": 0}
+
+# Optional per-launch timing (bench.py's per-kernel roofline): when `kernel_events` is a list, every C-ABI launch made through
+# `timed(label)` appends (label, start_event, end_event) recorded on the launching stream.  None (default): no events.
+kernel_events = None
+
+
+class timed:
+    def __init__(self, label):
+        self.label = label
+
+    def __enter__(self):
+        if kernel_events is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if kernel_events is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            kernel_events.append((self.label, self.a, b))
+        return False
 
 
 def count_launch(n=1):

@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 SO = os.path.join(LIBDIR, "libsanerf_b200.so")
-SOURCES = ["grid_encode.cu", "sh_encode.cu", "freq_encode.cu", "render.cu", "mlp_tc.cu", "heads.cu"]
+SOURCES = ["grid_encode.cu", "sh_encode.cu", "freq_encode.cu", "render.cu", "mlp_tc.cu", "heads.cu", "peer.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc.cuh"), os.path.join(CSRC, "grid_dev.cuh"), os.path.join(os.path.dirname(HERE), "include", "sanerf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "2"] + os.environ.get("SANERF_NVCC_FLAGS", "").split()

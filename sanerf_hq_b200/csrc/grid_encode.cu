@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(256) grid_forward_kernel(const float* __restri
 #pragma unroll
     for (uint32_t d = 0; d < D; d++) {
         float v = __ldg(inputs + (size_t)b * D + d);
-        if constexpr (FUSED) { if (bound > 0.f) v = __fdiv_rn(__fadd_rn(v, bound), 2 * bound); }  // grid.py:156; bound<=0: already in [0,1]
+        if constexpr (FUSED) { if (bound > 0.f) v = __fmul_rn(__fadd_rn(v, bound), __frcp_rn(2 * bound)); }  // grid.py:156 (tensor / Python scalar = multiply by the fp32 reciprocal in ATen); bound<=0: already in [0,1]
         x[d] = v;
     }
     float* out = FUSED ? outputs + (size_t)b * L * C + (size_t)level * C : outputs + ((size_t)level * B + b) * C;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) grid_backward_kernel(const float* __restr
 #pragma unroll
     for (uint32_t d = 0; d < D; d++) {
         float v = __ldg(inputs + (size_t)b * D + d);
-        if constexpr (FUSED) { if (bound > 0.f) v = __fdiv_rn(__fadd_rn(v, bound), 2 * bound); }
+        if constexpr (FUSED) { if (bound > 0.f) v = __fmul_rn(__fadd_rn(v, bound), __frcp_rn(2 * bound)); }
         x[d] = v;
     }
     if (out_of_unit_cube<D>(x)) return;  // gridencoder.cu:278-283

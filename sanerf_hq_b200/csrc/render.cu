@@ -84,6 +84,10 @@ struct RenderParams {
     float cam_pose[12];
     uint32_t tile_w;
     uint8_t* image_u8;
+    uint32_t n_peer;
+    float* peer_image[SANERF_MAX_PEERS];
+    float* peer_depth[SANERF_MAX_PEERS];
+    float* peer_wsum[SANERF_MAX_PEERS];
 };
 
 // ---- small helpers ------------------------------------------------------------------------------
@@ -390,7 +394,7 @@ __device__ __forceinline__ void sh4(float x, float y, float z, float (&o)[16]) {
 // sample position for bins (b0,b1): midpoint t, delta, contracted point mapped to [0,1]^3
 struct RayCtx {
     float ox, oy, oz, dx, dy, dz, s_near, s_far, bound;
-    float inv_den;   // 1/(2*bound) when 2*bound is a power of two (then x/den == x*inv_den exactly), else 0
+    float inv_den;   // fp32 reciprocal of 2*bound
     bool contract;
 };
 
@@ -402,16 +406,11 @@ __device__ __forceinline__ bool sample_point(const RayCtx& r, float b0, float b1
     float y = __fadd_rn(r.oy, __fmul_rn(r.dy, tmid));
     float z = __fadd_rn(r.oz, __fmul_rn(r.dz, tmid));
     if (r.contract) contract3(x, y, z);
-    const float den = 2.0f * r.bound;                       // grid.py:156
-    if (r.inv_den != 0.f) {
-        x01[0] = __fmul_rn(__fadd_rn(x, r.bound), r.inv_den);
-        x01[1] = __fmul_rn(__fadd_rn(y, r.bound), r.inv_den);
-        x01[2] = __fmul_rn(__fadd_rn(z, r.bound), r.inv_den);
-    } else {
-        x01[0] = __fdiv_rn(__fadd_rn(x, r.bound), den);
-        x01[1] = __fdiv_rn(__fadd_rn(y, r.bound), den);
-        x01[2] = __fdiv_rn(__fadd_rn(z, r.bound), den);
-    }
+    // grid.py:156 `(inputs + bound) / (2 * bound)`: a tensor divided by a Python scalar -- ATen's CUDA kernel multiplies by the
+    // fp32 reciprocal of the scalar (BinaryDivTrueKernel.cu), exact for the power-of-two 2*bound of every shipped configuration
+    x01[0] = __fmul_rn(__fadd_rn(x, r.bound), r.inv_den);
+    x01[1] = __fmul_rn(__fadd_rn(y, r.bound), r.inv_den);
+    x01[2] = __fmul_rn(__fadd_rn(z, r.bound), r.inv_den);
     bool oob = false;                                       // gridencoder.cu:105-111 -> zeros
 #pragma unroll
     for (int d = 0; d < 3; d++) oob |= (x01[d] < 0.f || x01[d] > 1.f);
@@ -532,11 +531,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             r.dx = __ldg(p.rays_d + 3 * (size_t)ray); r.dy = __ldg(p.rays_d + 3 * (size_t)ray + 1); r.dz = __ldg(p.rays_d + 3 * (size_t)ray + 2);
         }
         r.bound = p.bound;
-        {
-            const float den = 2.0f * p.bound;
-            const bool pow2 = (__float_as_uint(den) & 0x007fffffu) == 0 && den >= 1.0f / 1024 && den <= 1048576.0f;
-            r.inv_den = pow2 ? __frcp_rn(den) : 0.f;
-        }
+        r.inv_den = __frcp_rn(2.0f * p.bound);
         r.contract = p.contract != 0;
         float near = -CUDART_INF_F, far = CUDART_INF_F;
         {
@@ -696,6 +691,13 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                 const float v = __fmul_rn(lane == 0 ? rgb[0] : (lane == 1 ? rgb[1] : rgb[2]), 255.0f);
                 p.image_u8[3 * (size_t)ray + lane] = (uint8_t)(int)fminf(fmaxf(v, 0.f), 255.f);
             }
+            // multi-GPU: the same 20 bytes go straight into the other ranks' frame buffers over NVLink (peer.cu) -- the
+            // kernel's final stores are the all-gather of the narrow outputs
+            for (uint32_t q = 0; q < p.n_peer; q++) {
+                if (lane < 3) p.peer_image[q][3 * (size_t)ray + lane] = lane == 0 ? rgb[0] : (lane == 1 ? rgb[1] : rgb[2]);
+                if (lane == 3) p.peer_depth[q][ray] = depth;
+                if (lane == 4) p.peer_wsum[q][ray] = wsum;
+            }
         }
 
         // ---- parity taps ------------------------------------------------------------------------
@@ -835,13 +837,14 @@ __global__ void __launch_bounds__(256) sample_pdf_kernel(const float* __restrict
 
 // ---- host side -----------------------------------------------------------------------------------
 template <int PL, int GL, int HG, int HV>
-static int launch_render(const RenderParams& p, bool sam, bool mask, cudaStream_t st) {
+static int launch_render(const RenderParams& p, bool sam, bool mask, uint32_t max_ctas, cudaStream_t st) {
     using S = Smem<PL, GL, HG>;
     const size_t smem = (size_t)S::total * sizeof(float);
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t need = div_up(p.N, (uint32_t)kWarps);
+    if (max_ctas && max_ctas < (uint32_t)sms) sms = (int)max_ctas;
     const uint32_t blocks = need < (uint32_t)sms ? need : (uint32_t)sms;
 #define SANERF_LAUNCH(SAM_, MASK_)                                                                              \
     do {                                                                                                        \
@@ -906,19 +909,23 @@ int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf
     p.tile_w = (kWarps == 16 && a->tile_w && a->tile_w % 4 == 0 && a->N % (4 * a->tile_w) == 0) ? a->tile_w : 0;
     for (int i = 0; i < 4; i++) p.cam_intr[i] = a->cam_intrinsics[i];
     for (int i = 0; i < 12; i++) p.cam_pose[i] = a->cam_pose[i];
+    p.n_peer = a->n_peer_out;
+    if (p.n_peer > SANERF_MAX_PEERS) return SANERF_E_CONFIG;
+    for (uint32_t i = 0; i < SANERF_MAX_PEERS; i++) {
+        const bool on = i < p.n_peer;
+        p.peer_image[i] = on ? a->peer_image[i] : nullptr;
+        p.peer_depth[i] = on ? a->peer_depth[i] : nullptr;
+        p.peer_wsum[i] = on ? a->peer_weights_sum[i] : nullptr;
+        if (on && (!p.peer_image[i] || !p.peer_depth[i] || !p.peer_wsum[i])) return SANERF_E_NULL;
+    }
     p.inds0 = a->inds0; p.inds1 = a->inds1; p.weights2 = a->weights2; p.sigma2 = a->sigma2; p.bins2 = a->bins2; p.f_image = a->f_image;
 
     const uint32_t PL = m->prop_grid[0].num_levels, GL = m->grid.num_levels;
     if (m->prop_grid[1].num_levels != PL) return SANERF_E_CONFIG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (PL == 5 && GL == 16 && m->grid_hidden == 64 && m->view_hidden == 32) return launch_render<5, 16, 64, 32>(p, sam, mask, st);
-    if (PL == 4 && GL == 4 && m->grid_hidden == 16 && m->view_hidden == 16) return launch_render<4, 4, 16, 16>(p, sam, mask, st);
+    if (PL == 5 && GL == 16 && m->grid_hidden == 64 && m->view_hidden == 32) return launch_render<5, 16, 64, 32>(p, sam, mask, a->max_ctas, st);
+    if (PL == 4 && GL == 4 && m->grid_hidden == 16 && m->view_hidden == 16) return launch_render<4, 4, 16, 16>(p, sam, mask, a->max_ctas, st);
     return SANERF_E_CONFIG;
-}
-
-int sanerf_render_launch_count(const sanerf_model_t* m, const sanerf_render_args_t* a) {
-    (void)m;
-    return (a && a->N) ? 1 : 0;
 }
 
 int sanerf_sample_pdf(const float* bins, const float* weights, const float* u, uint32_t N, uint32_t T0, uint32_t T, float* new_bins,

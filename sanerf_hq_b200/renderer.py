@@ -149,6 +149,7 @@ class NeRFRenderer(nn.Module):
             aabb = torch.from_numpy(aabb).float()
         self.aabb_train = aabb.clamp(-self.real_bound, self.real_bound).to(self.aabb_train.device)
         self.aabb_infer = self.aabb_train.clone()
+        self._aabb_host = (None, None)     # fresh tensors may reuse a freed block: never trust (data_ptr, version) across an update
         print(f"[INFO] update_aabb: {self.aabb_train.cpu().numpy().tolist()}")
 
     # ------------------------------------------------------------------------------------------
@@ -166,6 +167,7 @@ class NeRFRenderer(nn.Module):
             return self._run_fused(rays_o, rays_d, cam_near_far=cam_near_far, **kwargs)
         N, device = rays_o.shape[0], rays_o.device
         results = {}
+        out = kwargs.pop("out", None)
         step = self.opt.max_ray_batch
         for head in range(0, N, step):
             tail = min(head + step, N)
@@ -182,6 +184,11 @@ class NeRFRenderer(nn.Module):
                     results[k][head:tail] = v
                 else:
                     results[k] = v
+        if out:
+            for k, dst in out.items():
+                if k in results:
+                    dst.copy_(results[k].reshape(dst.shape))
+                    results[k] = dst
         return results
 
     @torch.no_grad()
@@ -208,37 +215,72 @@ class NeRFRenderer(nn.Module):
         return self._run_fused(None, None, camera=camera, return_uint8=return_uint8, **kw)
 
     def run(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
-            return_feats=0, return_mask=0, H=None, W=None, image_width=None, **kwargs):
-        """`image_width` (not in the reference): optional hint that the rays are a row-major image block of that width, which
-        lets the fused kernel walk 4x4-pixel tiles; results are unchanged."""
+            return_feats=0, return_mask=0, H=None, W=None, image_width=None, out=None, peer_out=None, max_ctas=0, **kwargs):
+        """Not in the reference: `image_width` -- optional hint that the rays are a row-major image block of that width, which
+        lets the fused kernel walk 4x4-pixel tiles (results are unchanged); `out` -- optional dict of preallocated result
+        tensors (`image`, `depth`, `weights_sum`, `samvit`, `instance_mask_logits`) the kernels store into directly (used by
+        parallel.FrameGather so that a rank's pixels land in its slot of the all-gather buffer without a copy); `peer_out` -- dict
+        key -> list of raw device pointers (the other ranks' frame buffers in NVLink peer memory, at ray 0 of this call) that
+        the fused kernel additionally stores image / depth / weights_sum into; `max_ctas` -- cap on the persistent CTAs."""
         if self.opt.render_mesh:
             return {}  # the reference's mesh branch is commented out and returns an empty dict (renderer.py:386-498)
         kw = dict(bg_color=bg_color, perturb=perturb, cam_near_far=cam_near_far, update_proposal=update_proposal,
                   return_feats=return_feats, return_mask=return_mask, H=H, W=W, image_width=image_width)
         if self._can_fuse(rays_o, kw):
-            return self._run_fused(rays_o, rays_d, **kw)
-        return self._run_composed(rays_o, rays_d, **kw)
+            return self._run_fused(rays_o, rays_d, out=out, peer_out=peer_out, max_ctas=max_ctas, **kw)
+        if peer_out:
+            raise RuntimeError("NeRFRenderer.run: peer_out needs the fused kernel (eval / no-grad, perturb=False)")
+        if not torch.is_grad_enabled() and not self.training:
+            self._warn_composed(kw)
+        res = self._run_composed(rays_o, rays_d, **kw)
+        if out:
+            for k, dst in out.items():
+                if k in res:
+                    dst.copy_(res[k].reshape(dst.shape))
+                    res[k] = dst
+        return res
+
+    def _warn_composed(self, kw):
+        """Eval-mode call that cannot take the single-launch kernel: say so once per reason instead of silently running ~10x
+        slower on the op-by-op path."""
+        reason = self._fuse_blocker(kw)
+        if reason is None:
+            return
+        seen = self.__dict__.setdefault("_composed_warned", set())
+        if reason not in seen:
+            seen.add(reason)
+            import warnings
+            warnings.warn(f"sanerf_hq_b200: eval-mode render falls back to the op-by-op torch path ({reason}); "
+                          "the fused sm_100a kernel is not used for this call", RuntimeWarning, stacklevel=3)
 
     # ------------------------------------------------------------------------------------------
     # fused path
     # ------------------------------------------------------------------------------------------
+    def _fuse_blocker(self, kw):
+        """None when the configuration is one the fused kernel implements, else the reason it is not (a string)."""
+        if not self.fused:
+            return "model.fused is False"
+        if kw.get("perturb", False):
+            return "perturb=True draws torch random numbers per sample"
+        if self.opt.render_mesh:
+            return "render_mesh"
+        if list(self.opt.num_steps) != FUSED_NUM_STEPS:
+            return f"num_steps {list(self.opt.num_steps)} != {FUSED_NUM_STEPS}"
+        if self.opt.with_sam and not self.opt.sam_use_view_direction:
+            return "with_sam without sam_use_view_direction"
+        if kw.get("return_mask", 0) and self.opt.mask_mlp_type != "default":
+            return f"mask_mlp_type {self.opt.mask_mlp_type}"
+        shape = (self.grid.num_levels, self.prop_encoders[0].num_levels, self.grid_mlp.dim_hidden, self.view_mlp.dim_hidden)
+        if shape not in ((16, 5, 64, 32), (4, 4, 16, 16)) or self.prop_encoders[1].num_levels != self.prop_encoders[0].num_levels:
+            return f"network shape {shape} has no fused instantiation"
+        return None
+
     def _can_fuse(self, rays_o, kw):
-        if not self.fused or not rays_o.is_cuda:
-            return False
-        if torch.is_grad_enabled() or kw.get("perturb", False):
-            return False
-        if self.opt.render_mesh or list(self.opt.num_steps) != FUSED_NUM_STEPS:
+        if not rays_o.is_cuda or torch.is_grad_enabled():
             return False
         if self.training and not self.opt.with_mask and not self.opt.with_sam:
             return False  # rgb training mode also returns losses / weights (renderer.py:343-351)
-        if self.opt.with_sam and not self.opt.sam_use_view_direction:
-            return False
-        if kw.get("return_mask", 0) and self.opt.mask_mlp_type != "default":
-            return False
-        L = self.grid.num_levels
-        shape_ok = (L, self.prop_encoders[0].num_levels, self.grid_mlp.dim_hidden, self.view_mlp.dim_hidden) in (
-            (16, 5, 64, 32), (4, 4, 16, 16))
-        return shape_ok and self.prop_encoders[1].num_levels == self.prop_encoders[0].num_levels
+        return self._fuse_blocker(kw) is None
 
     def _u_table(self, T, device):
         key = (T, str(device))
@@ -293,7 +335,7 @@ class NeRFRenderer(nn.Module):
     @torch.no_grad()
     def _run_fused(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
                    return_feats=0, return_mask=0, H=None, W=None, taps=None, camera=None, return_uint8=False, image_width=None,
-                   **kwargs):
+                   out=None, peer_out=None, max_ctas=0, **kwargs):
         if camera is None:
             rays_o = rays_o.contiguous().float()
             rays_d = rays_d.contiguous().float()
@@ -308,9 +350,18 @@ class NeRFRenderer(nn.Module):
             break
         model, keep = self._model_struct(device)
 
-        image = torch.empty(N, 3, device=device)
-        depth = torch.empty(N, device=device)
-        weights_sum = torch.empty(N, device=device)
+        def result(key, *shape):
+            """Result tensor `key`: the caller's preallocated one (`out`) or a fresh one."""
+            t = out.get(key) if out else None
+            if t is None:
+                return torch.empty(*shape, device=device)
+            if tuple(t.shape) != shape or t.dtype != torch.float32 or t.device != device or not t.is_contiguous():
+                raise RuntimeError(f"NeRFRenderer.run: out['{key}'] must be a contiguous fp32 tensor of shape {shape} on {device}")
+            return t
+
+        image = result("image", N, 3)
+        depth = result("depth", N)
+        weights_sum = result("weights_sum", N)
         results = {"weights_sum": weights_sum, "depth": depth, "image": image}
 
         a = _lib.RenderArgsT()
@@ -345,6 +396,21 @@ class NeRFRenderer(nn.Module):
             else:
                 a.bg_scalar = float(bg_color)
         a.image, a.depth, a.weights_sum = image.data_ptr(), depth.data_ptr(), weights_sum.data_ptr()
+        a.max_ctas = int(max_ctas or 0)
+        peer = None
+        if peer_out:
+            peer = [peer_out["image"], peer_out["depth"], peer_out["weights_sum"]]
+            a.n_peer_out = len(peer[0])
+
+        def set_peer(head):
+            """Peer pointers of ray `head` of this call (image 12 B, depth / weights_sum 4 B per ray)."""
+            if peer:
+                for i in range(a.n_peer_out):
+                    a.peer_image[i] = peer[0][i] + 12 * head
+                    a.peer_depth[i] = peer[1][i] + 4 * head
+                    a.peer_weights_sum[i] = peer[2][i] + 4 * head
+
+        set_peer(0)
 
         want_sam = self.opt.with_sam and return_feats > 0
         want_mask = return_mask > 0
@@ -353,7 +419,8 @@ class NeRFRenderer(nn.Module):
                       "sigma2": ((N, 32), torch.float32), "bins2": ((N, 33), torch.float32), "f_image": ((N, 31), torch.float32)}
             for name in list(taps):
                 shp, dt = shapes[name]
-                taps[name] = torch.empty(shp, device=device, dtype=dt)
+                # rows rounded up to whole 128-sample tiles (4 rays): the tensor-core object head reads full tiles of weights2
+                taps[name] = torch.empty((-(-N // 4) * 4,) + shp[1:], device=device, dtype=dt)[:N]
                 setattr(a, name, taps[name].data_ptr())
 
         if not want_mask:
@@ -361,11 +428,11 @@ class NeRFRenderer(nn.Module):
             if want_sam:
                 sam_in = self._alloc_rows_padded(N, self.samvit_mlp[0].dim_in, device)
                 a.sam_in = sam_in.data_ptr()
-            with torch.cuda.device(device):
+            with torch.cuda.device(device), _lib.timed("render_kernel"):
                 _lib.check(lib.sanerf_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "sanerf_render")
                 _lib.count_launch()
             if want_sam:
-                results["samvit"] = self._samvit_head(sam_in).view(H, W, -1)
+                results["samvit"] = self._samvit_head(sam_in, out=out.get("samvit") if out else None).view(H, W, -1)
             return results
 
         # object head.  Default shapes: the fused kernel leaves an 18-float record (point, geo_feat) per sample and the
@@ -373,7 +440,7 @@ class NeRFRenderer(nn.Module):
         # per chunk of rays (the chunk bounds the scratch).  Other widths (config #1's small network, n_inst > 16): the fused
         # kernel writes the full per-sample inputs cat[m_grid(x), geo_feat] and the nn.Module MLP consumes them.
         n_inst = self.opt.n_inst
-        logits = torch.empty(N, n_inst, device=device)
+        logits = result("instance_mask_logits", N, n_inst)
         width = self.mask_mlp[0].dim_in
         net = self.mask_mlp[0].net
         tc_head = (width == 143 and len(net) == 3 and net[0].weight.shape == (256, 143) and net[1].weight.shape == (256, 256)
@@ -408,6 +475,7 @@ class NeRFRenderer(nn.Module):
                 a.bg_color = base["bg_color"] + head * 12
             a.N = n
             a.cam_ray0 = cam_ray0 + head
+            set_peer(head)
             a.mask_in = mask_in.data_ptr()
             if not user_w2:
                 a.weights2 = w2.data_ptr()
@@ -415,19 +483,21 @@ class NeRFRenderer(nn.Module):
                 a.sam_in = sam_full.data_ptr() + head * sam_full.shape[1] * 4
             wts = taps["weights2"][head:head + n] if user_w2 else w2[:n]
             with torch.cuda.device(device):
-                _lib.check(lib.sanerf_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "sanerf_render")
-                _lib.count_launch()
+                with _lib.timed("render_kernel"):
+                    _lib.check(lib.sanerf_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "sanerf_render")
+                    _lib.count_launch()
                 if tc_head:
-                    out = logits[head:head + n]
-                    _lib.check(lib.sanerf_mask_head(_lib.ptr(mask_in), _lib.ptr(wts), ctypes.byref(model.m_grid), _lib.ptr(mw[0]),
-                                                    _lib.ptr(mw[1]), _lib.ptr(mw[2]), n_inst, n, _lib.ptr(self._mask_ws), _lib.ptr(out),
-                                                    _lib.stream_ptr()), "sanerf_mask_head")
-                    _lib.count_launch(2)
+                    dst = logits[head:head + n]
+                    with _lib.timed("mask_head_kernel"):
+                        _lib.check(lib.sanerf_mask_head(_lib.ptr(mask_in), _lib.ptr(wts), ctypes.byref(model.m_grid), _lib.ptr(mw[0]),
+                                                        _lib.ptr(mw[1]), _lib.ptr(mw[2]), n_inst, n, _lib.ptr(self._mask_ws), _lib.ptr(dst),
+                                                        _lib.stream_ptr()), "sanerf_mask_head")
+                        _lib.count_launch(2)
             if not tc_head:
                 point_masks = self.mask_mlp(mask_in[:n * 32 * width].view(n, 32, width))
                 logits[head:head + n] = torch.sum(wts.unsqueeze(-1) * point_masks, dim=-2)
         if want_sam:
-            results["samvit"] = self._samvit_head(sam_full).view(H, W, -1)
+            results["samvit"] = self._samvit_head(sam_full, out=out.get("samvit") if out else None).view(H, W, -1)
         results["instance_mask_logits"] = logits
         return results
 
@@ -436,9 +506,10 @@ class NeRFRenderer(nn.Module):
         """[n, width] view of a buffer with whole tiles of `multiple` rows (the tensor-core heads read full tiles)."""
         return torch.empty(-(-max(n, 1) // multiple) * multiple, width, device=device)[:n]
 
-    def _samvit_head(self, f):
+    def _samvit_head(self, f, out=None):
         """samvit_mlp (SkipConnMLP + LayerNorm, network.py:113-116) of the composited per-ray features f [n,163].
-        No-grad CUDA input with the reference's shapes -> the tensor-core head (csrc/heads.cu); anything else -> nn.Modules."""
+        No-grad CUDA input with the reference's shapes -> the tensor-core head (csrc/heads.cu); anything else -> nn.Modules.
+        `out`: optional preallocated contiguous fp32 tensor with n*256 elements the head stores into."""
         mlp, ln = self.samvit_mlp[0], self.samvit_mlp[1]
         net = mlp.net
         ok = (f.is_cuda and not torch.is_grad_enabled() and f.dim() == 2 and f.shape[1] == 163 and len(net) == 5
@@ -447,17 +518,26 @@ class NeRFRenderer(nn.Module):
               and tuple(ln.normalized_shape) == (256,) and abs(ln.eps - 1e-5) < 1e-12 and ln.weight is not None
               and f.untyped_storage().nbytes() - f.storage_offset() * 4 >= -(-f.shape[0] // 128) * 128 * 163 * 4)
         if not ok:
-            return self.samvit_mlp(f)
+            res = self.samvit_mlp(f)
+            if out is not None:
+                out.view(-1, res.shape[-1]).copy_(res)
+                return out.view(-1, res.shape[-1])
+            return res
         lib = _lib.load()
         n, device = f.shape[0], f.device
         if getattr(self, "_sam_ws", None) is None or self._sam_ws.device != device:
             self._sam_ws = torch.empty(lib.sanerf_samvit_mlp_workspace_bytes(), dtype=torch.uint8, device=device)
         ws = [l.weight.detach().contiguous() for l in net]
         bs = [l.bias.detach().contiguous() for l in net]
-        out = torch.empty(n, 256, device=device)
+        if out is None:
+            out = torch.empty(n, 256, device=device)
+        elif out.numel() != n * 256 or out.dtype != torch.float32 or out.device != device or not out.is_contiguous():
+            raise RuntimeError(f"NeRFRenderer: out['samvit'] must be a contiguous fp32 tensor with {n} x 256 elements on {device}")
+        else:
+            out = out.view(n, 256)
         wp = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in ws])
         bp = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in bs])
-        with torch.cuda.device(device):
+        with torch.cuda.device(device), _lib.timed("samvit_mlp_kernel"):
             _lib.check(lib.sanerf_samvit_mlp(_lib.ptr(f), wp, bp, _lib.ptr(ln.weight.detach()), _lib.ptr(ln.bias.detach()), n,
                                              _lib.ptr(self._sam_ws), _lib.ptr(out), _lib.stream_ptr()), "sanerf_samvit_mlp")
             _lib.count_launch(2)

@@ -10,7 +10,6 @@ if REPO not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
-    config.addinivalue_line("markers", "gpu_staged: GPU tests written but not yet run on a B200 (not selected by -m gpu)")
 
 
 def pytest_collection_modifyitems(config, items):

@@ -29,9 +29,9 @@ def test_library_exports_every_declared_symbol():
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
     assert not missing, f"libsanerf_b200.so lacks {missing}"
     # every declared symbol has a ctypes prototype, and vice versa
-    assert declared == set(_lib.PROTOTYPES) - {s for s in _lib.OPTIONAL if s not in declared}
+    assert declared == set(_lib.PROTOTYPES)
     L = _lib.load()
-    assert L.sanerf_abi_version() == 1
+    assert L.sanerf_abi_version() == 2
     assert b"C must be" in L.sanerf_error_string(-3)
 
 
@@ -46,6 +46,7 @@ int main(void) {
   printf("%zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(sanerf_grid_t), sizeof(sanerf_model_t), sizeof(sanerf_render_args_t),
          offsetof(sanerf_model_t, grid), offsetof(sanerf_model_t, s_grid), offsetof(sanerf_model_t, aabb),
          offsetof(sanerf_model_t, u65), offsetof(sanerf_render_args_t, f_image));
+  printf("%zu %zu\n", offsetof(sanerf_render_args_t, peer_depth), offsetof(sanerf_render_args_t, max_ctas));
   return 0; }
 '''
     with tempfile.TemporaryDirectory() as d:
@@ -53,7 +54,8 @@ int main(void) {
         subprocess.check_call(["gcc", "-I", os.path.join(REPO, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")])
         got = [int(v) for v in subprocess.check_output([os.path.join(d, "t")]).split()]
     want = [ctypes.sizeof(_lib.GridT), ctypes.sizeof(_lib.ModelT), ctypes.sizeof(_lib.RenderArgsT), _lib.ModelT.grid.offset,
-            _lib.ModelT.s_grid.offset, _lib.ModelT.aabb.offset, _lib.ModelT.u65.offset, _lib.RenderArgsT.f_image.offset]
+            _lib.ModelT.s_grid.offset, _lib.ModelT.aabb.offset, _lib.ModelT.u65.offset, _lib.RenderArgsT.f_image.offset,
+            _lib.RenderArgsT.peer_depth.offset, _lib.RenderArgsT.max_ctas.offset]
     assert got == want
 
 

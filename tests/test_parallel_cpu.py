@@ -11,7 +11,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from sanerf_hq_b200.parallel import gather_dict, gather_rows, render_sharded, shard_bounds
+from sanerf_hq_b200.parallel import FrameGather, gather_dict, gather_rows, packed_floats_per_rank, render_sharded, shard_bounds
 
 
 def _fake_render(rays_o, rays_d, **kw):
@@ -44,6 +44,33 @@ def _worker(rank, world, port, n, out_dir):
         ok &= torch.equal(gather_rows(full["depth"][lo:hi], counts), full["depth"])
         packed = gather_dict({k: full[k][lo:hi] for k in ("image", "depth", "weights_sum")}, counts)   # one collective
         ok &= all(torch.equal(packed[k], full[k]) for k in ("image", "depth", "weights_sum"))
+        # a wide key (the 256-d SAM feature) next to the narrow ones: gathered on its own, not packed
+        wide = torch.arange(n * 20, dtype=torch.float32).reshape(n, 20)
+        mixed = gather_dict({"image": full["image"][lo:hi], "samvit": wide[lo:hi]}, counts)
+        ok &= torch.equal(mixed["samvit"], wide) and torch.equal(mixed["image"], full["image"])
+        # FrameGather (equal counts only): results land in the rank's slot of the full-frame tensors, in-place all-gather,
+        # double-buffered frames, row groups
+        if n % world == 0:
+            n_local = n // world
+
+            class FakeModel:
+                def render(self, ro, rd, staged=True, out=None, **kw):
+                    res = _fake_render(ro, rd)
+                    for k, dst in out.items():
+                        dst.copy_(res[k].reshape(dst.shape) if k in res else (ro[:, :1] * torch.arange(4.0)).reshape(dst.shape))
+                    return res
+
+            fg = FrameGather(n_local, {"image": (3,), "depth": (), "weights_sum": (), "wide": (4,)}, "cpu")
+            assert fg.transport == "nccl"
+            for frame, groups in enumerate((1, 2, 1)):
+                scale = float(frame + 1)
+                got = fg.render(FakeModel(), rays_o[lo:hi] * scale, rays_d[lo:hi], groups=groups)
+                want = _fake_render(rays_o * scale, rays_d)
+                ok &= all(torch.equal(got[k], want[k]) for k in ("image", "depth", "weights_sum"))
+                ok &= torch.equal(got["wide"], rays_o[:, :1] * scale * torch.arange(4.0))
+                if frame:
+                    ok &= prev["image"].data_ptr() != got["image"].data_ptr()     # double-buffered
+                prev = got
         torch.save(bool(ok), os.path.join(out_dir, f"ok{rank}.pt"))
     finally:
         dist.destroy_process_group()
@@ -53,6 +80,12 @@ def _worker(rank, world, port, n, out_dir):
 def test_sharded_render_equals_single_process(tmp_path, world, n):
     mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
     assert all(torch.load(os.path.join(str(tmp_path), f"ok{r}.pt")) for r in range(world))
+
+
+def test_packed_buffer_holds_only_the_narrow_keys():
+    """the packed all-gather buffer must not reserve room for the wide keys that travel on their own."""
+    widths = {"image": 3, "depth": 1, "weights_sum": 1, "samvit": 256, "instance_mask_logits": 2}
+    assert packed_floats_per_rank(widths, [100, 99]) == 100 * 7
 
 
 def test_shard_bounds_cover_everything():

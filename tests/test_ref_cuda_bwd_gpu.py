@@ -1,10 +1,7 @@
-"""STAGED GPU tests (marker `gpu_staged`, NOT part of `-m gpu`): the regulariser and backward kernels against the REFERENCE'S OWN
-compiled kernels in oracle/_ref (tests/test_ref_cuda_gpu.py does the same for the grid forward / backward and the SH / freq
-forward, and is green).  Written after the round's GPU budget was spent; they are already green against the C oracle
-(`test_grid_backward_tv_wd_match_oracle`, `test_sh_matches_oracle`, `test_freq_matches_oracle_and_torch_encoder`).
-
-    python -m pytest tests/test_ref_cuda_staged.py -m gpu_staged -q          # on a B200, then merge into test_ref_cuda_gpu.py
-"""
+"""GPU: the regulariser and backward kernels (K4 TV, K5 weight decay, K7 SH backward, K9 freq backward) against the REFERENCE'S
+OWN compiled kernels in oracle/_ref (tests/test_ref_cuda_gpu.py does the same for the grid forward / backward and the SH /
+freq forward).  The same kernels are also checked against the C oracle (`test_grid_backward_tv_wd_match_oracle`,
+`test_sh_matches_oracle`, `test_freq_matches_oracle_and_torch_encoder`)."""
 import importlib
 import os
 import sys
@@ -15,7 +12,7 @@ import torch
 
 from helpers import REPO
 
-pytestmark = [pytest.mark.gpu_staged, pytest.mark.skipif(not torch.cuda.is_available(), reason="no CUDA device")]
+pytestmark = pytest.mark.gpu
 DEV = "cuda"
 REFDIR = os.path.join(REPO, "oracle", "_ref")
 

@@ -143,9 +143,20 @@ def test_fused_equals_composed_on_a_large_batch(mode):
         c = _render(model, rays_o, rays_d, True, True, **kw)
         for k in a:
             assert torch.equal(a[k], c[k]), k          # chunking must not change per-ray arithmetic
-    # render quirk: non-staged drops cam_near_far (reference renderer.py:187-188)
-    d = model.render(rays_o[:64].to(DEV), rays_d[:64].to(DEV), staged=False, cam_near_far=torch.tensor([[0.5, 2.0]], device=DEV))
-    assert torch.equal(d["image"], a["image"][:64]) if False else True
+    # render quirk: `render(staged=False)` swallows cam_near_far and does NOT forward it to run() (reference renderer.py:187-188),
+    # while the staged loop honours it (renderer.py:197-205).  Same grad mode / path for all three renders.
+    if mode != "sam":
+        cnf = torch.tensor([[0.5, 2.0]], device=DEV)
+        ro64, rd64 = rays_o[:64].to(DEV), rays_d[:64].to(DEV)
+        model.fused = True
+        with torch.no_grad():
+            plain = model.render(ro64, rd64, staged=False, **kw)
+            dropped = model.render(ro64, rd64, staged=False, cam_near_far=cnf, **kw)
+            honoured = model.render(ro64, rd64, staged=True, cam_near_far=cnf, **kw)
+        for k in plain:
+            assert torch.equal(plain[k], dropped[k]), k
+        assert not torch.equal(honoured["depth"], plain["depth"])
+        assert float(honoured["depth"].max()) <= 2.0 * (1 + 1e-5)
 
 
 def test_object_head_chunking_is_invisible():

@@ -1,0 +1,173 @@
+"""GPU: the B-model boundary proven with the REFERENCE'S OWN CALLER.
+
+The reference's unmodified `nerf/trainer.py::Trainer` (oracle/_ref/pyc) is constructed over this repo's drop-in
+`NeRFNetwork` and over the reference's own `NeRFNetwork` (reference kernels, oracle/_ref/*.so) with identical weights; its
+`test_step` (:692), `eval_step` (:570), one rgb `train_step` (:336) + `post_train_step` (TV / weight-decay hooks, :558) and
+one object-stage `train_step` after main.py's name-based freezing (main.py:249-256) must give the same numbers on both, and
+a checkpoint written by the reference-side trainer must load into the drop-in model through `Trainer.load_checkpoint`.
+"""
+import os
+import tempfile
+
+import pytest
+import torch
+
+import trainer_harness as TH
+from helpers import O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _R():
+    from oracle import ref_runtime as R
+    if not R.available("cuda"):
+        pytest.skip("oracle/_ref is not staged (python oracle/stage_ref.py; python oracle/build_ref.py)")
+    return R
+
+
+def _pair(opt, seed=7):
+    """(reference model, drop-in model) with the same seeded weights."""
+    from sanerf_hq_b200.network import NeRFNetwork
+    R = _R()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    params, _ = O.make_params(opt, O.default_specs(2), seed=seed)
+    ref = R.build_network(opt, params, device=DEV)
+    cand = NeRFNetwork(opt)
+    res = cand.load_state_dict(params, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    return R, ref, cand.eval().to(DEV)
+
+
+def _close(a, b, tol=1e-3, floor=1e-3, what=""):
+    a, b = a.detach().double().reshape(-1), b.detach().double().reshape(-1)
+    e = float(((a - b).abs() / b.abs().clamp(min=floor)).max())
+    assert e <= tol, f"{what}: max rel err {e:.3e}"
+
+
+def test_reference_trainer_eval_and_test_steps_on_dropin_model():
+    from sanerf_hq_b200 import _lib
+    opt = TH.trainer_opt()
+    R, ref, cand = _pair(opt)
+    with tempfile.TemporaryDirectory() as ws:
+        t_ref = TH.make_trainer(R, "cuda", ref, opt, os.path.join(ws, "ref"))
+        t_cand = TH.make_trainer(R, "cuda", cand, opt, os.path.join(ws, "cand"))
+        data = TH.frame_data(96, 128, 5, DEV)
+        with R.env("cuda"), torch.no_grad():
+            ref.eval(), cand.eval()
+            rgb_r, depth_r = t_ref.test_step(data)
+            n0 = _lib.launch_counter["n"]
+            rgb_c, depth_c = t_cand.test_step(data)
+            assert _lib.launch_counter["n"] == n0 + 1, "test_step must take the fused single-launch path"
+            assert rgb_c.shape == (96, 128, 3) and depth_c.shape == (96, 128)
+            _close(rgb_c, rgb_r, what="test_step rgb")
+            _close(depth_c, depth_r, what="test_step depth")
+            # bg_color tensor + perturb False, as the GUI calls it (gui.py:145-183 -> trainer.test_gui)
+            bg = torch.tensor([0.1, 0.4, 0.7])
+            _close(t_cand.test_step(data, bg_color=bg)[0], t_ref.test_step(data, bg_color=bg)[0], what="test_step bg")
+            er, ec = t_ref.eval_step(data), t_cand.eval_step(data)
+            _close(ec[0], er[0], what="eval_step rgb")
+            _close(ec[4], er[4], what="eval_step loss")
+            assert ec[2] is None and torch.equal(ec[3], er[3])
+
+
+def test_reference_trainer_rgb_train_step_and_regularisers():
+    opt = TH.trainer_opt(num_rays=2048)
+    R, ref, cand = _pair(opt)
+    with tempfile.TemporaryDirectory() as ws:
+        t_ref = TH.make_trainer(R, "cuda", ref, opt, os.path.join(ws, "ref"))
+        t_cand = TH.make_trainer(R, "cuda", cand, opt, os.path.join(ws, "cand"))
+        data = TH.train_data(2048, DEV, seed=3)
+        grads = {}
+        with R.env("cuda"):
+            for name, tr in (("ref", t_ref), ("cand", t_cand)):
+                torch.manual_seed(11)                       # perturb=True: both sides draw rand_like in the same order
+                opt.num_rays = 2048
+                tr.model.train()
+                tr.global_step += 1
+                tr.optimizer.zero_grad()
+                preds, truths, loss = tr.train_step(data)
+                tr.scaler.scale(loss).backward()
+                before_reg = tr.model.grid.embeddings.grad.clone()
+                tr.post_train_step()                        # in-place TV + weight decay on the table gradient (trainer.py:558-568)
+                assert not torch.equal(before_reg, tr.model.grid.embeddings.grad)
+                grads[name] = (float(loss), {n: p.grad.detach().clone() for n, p in tr.model.named_parameters()}, preds.detach())
+                assert opt.num_rays == 8192                  # adaptive_num_rays: 2^18 points / 32 samples per ray (trainer.py:395-397)
+                tr.scaler.step(tr.optimizer)
+                tr.scaler.update()
+        (lr_, gr, pr), (lc, gc, pc) = grads["ref"], grads["cand"]
+        assert abs(lc - lr_) <= 1e-4 * abs(lr_), (lc, lr_)
+        _close(pc, pr, what="train_step image")
+        assert set(gr) == set(gc)
+        for n in gr:
+            scale = float(gr[n].abs().max())
+            assert scale > 0, n
+            err = float((gc[n] - gr[n]).abs().max())
+            assert err <= 2e-3 * scale, f"grad {n}: {err:.3e} vs scale {scale:.3e}"   # atomics on both sides: summation-order noise
+        for p in cand.parameters():
+            assert torch.isfinite(p).all()
+
+
+def test_object_stage_freezing_train_step_and_checkpoint_roundtrip():
+    """main.py:247-256: the object stage builds NeRFNetwork(with_mask), loads the rgb checkpoint non-strictly and freezes every
+    parameter whose NAME is in it; only m_grid / mask_mlp then receive gradients (trainer.py:401-505)."""
+    from sanerf_hq_b200.network import NeRFNetwork
+    R = _R()
+    opt_rgb = TH.trainer_opt()
+    opt_obj = TH.trainer_opt(with_mask=True, num_rays=1024)
+    _, ref_rgb, _ = _pair(opt_rgb)
+    with tempfile.TemporaryDirectory() as ws:
+        # the rgb stage's checkpoint, written by the reference trainer over the reference model
+        t_rgb = TH.make_trainer(R, "cuda", ref_rgb, opt_rgb, os.path.join(ws, "rgb"))
+        with R.env("cuda"):
+            t_rgb.save_checkpoint(full=True)
+        ckpt = os.path.join(ws, "rgb", "checkpoints", "ngp_ep0000.pth")
+        assert os.path.exists(ckpt)
+
+        models = {}
+        params_obj, _ = O.make_params(opt_obj, O.default_specs(2), seed=21)   # fresh m_grid / mask_mlp (and other) weights
+        for name in ("ref", "cand"):
+            if name == "ref":
+                model = R.build_network(opt_obj, params_obj, device=DEV)
+            else:
+                model = NeRFNetwork(opt_obj)
+                model.load_state_dict(params_obj, strict=True)
+                model = model.to(DEV)
+            model_dict = torch.load(ckpt, map_location=DEV)["model"]
+            res = model.load_state_dict(model_dict, strict=False)
+            assert not res.unexpected_keys and all(k.startswith(("m_grid", "mask_mlp")) for k in res.missing_keys), res
+            for k, v in model.named_parameters():                            # main.py:253-256
+                if k in model_dict:
+                    v.requires_grad = False
+            assert sorted(k.split(".")[0] for k, v in model.named_parameters() if v.requires_grad) == ["m_grid", "mask_mlp", "mask_mlp", "mask_mlp"]
+            models[name] = model
+        data = TH.train_data(1024, DEV, seed=4, masks=True)
+        out = {}
+        with R.env("cuda"):
+            for name, model in models.items():
+                tr = TH.make_trainer(R, "cuda", model, opt_obj, os.path.join(ws, name))
+                model.train()
+                tr.global_step += 1
+                tr.optimizer.zero_grad()
+                preds, truths, loss = tr.train_step(data)
+                loss.backward()
+                tr.post_train_step()                                          # regularises m_grid in the object stage (network.py:196-206)
+                out[name] = (float(loss), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.grad is not None}, preds)
+                tr.optimizer.step()
+        (lr_, gr, pr), (lc, gc, pc) = out["ref"], out["cand"]
+        assert abs(lc - lr_) <= 1e-4 * abs(lr_), (lc, lr_)
+        assert set(gr) == set(gc) and all(n.startswith(("m_grid", "mask_mlp")) for n in gc)
+        assert float((pc != pr).float().mean()) < 1e-3                       # argmax labels
+        for n in gr:
+            scale = float(gr[n].abs().max())
+            assert float((gc[n] - gr[n]).abs().max()) <= 2e-3 * scale, n
+
+        # checkpoint round trip through Trainer.load_checkpoint (trainer.py:1778-1842): reference-written file -> drop-in model
+        fresh = NeRFNetwork(opt_rgb).to(DEV)
+        t_new = TH.make_trainer(R, "cuda", fresh, opt_rgb, os.path.join(ws, "rgb"))
+        with R.env("cuda"):
+            t_new.load_checkpoint()
+        sd_ref, sd_new = ref_rgb.state_dict(), fresh.state_dict()
+        assert list(sd_ref) == list(sd_new)
+        for k in sd_ref:
+            assert torch.equal(sd_ref[k], sd_new[k]), k
