@@ -25,7 +25,7 @@ collective) and the composited frame is left on every rank through NVLink peer m
 peer stores + copy-engine pushes + one flag barrier; in-place NCCL all-gathers as the fallback) inside the timed region.
 
 --impl reference times the reference's own CPU implementation on the host cores: the reference's unmodified renderer / network
-Python (oracle/_ref/pyc) over the C restatement of its two CUDA-only encoder kernels (the reference has no CPU encoder), all
+Python (oracle/_ref/bytecode) over the C restatement of its two CUDA-only encoder kernels (the reference has no CPU encoder), all
 host threads, rank 0 only.
 """
 import argparse
@@ -139,9 +139,9 @@ _CPU_REF = {}
 
 def cpu_baseline(workload, model_sd, n_chunks, H, W, threads=None):
     """The reference's CPU path over `n_chunks` x 4096 rays of pose 0 (rows from the middle of the frame), all host threads.
-    kind "reference": the reference's own renderer.py / network.py (oracle/_ref/pyc, byte-compiled unmodified) with the C
+    kind "reference": the reference's own renderer.py / network.py (oracle/_ref/bytecode, byte-compiled unmodified) with the C
     restatement of its two CUDA-only encoder kernels behind its `_gridencoder` / `_shencoder` imports; kind "port": the
-    oracle's torch restatement of the same Python (when oracle/_ref/pyc is not staged).
+    oracle's torch restatement of the same Python (when oracle/_ref/bytecode is not staged).
     Returns (Mrays/s, cores, kind, sample description, seconds)."""
     from oracle import kernels as K
     from oracle import ref_runtime as R
@@ -203,7 +203,7 @@ def run_reference(args, rank):
         t_total += dt
         rays_total += int(round(mr * 1e6 * dt))
     value = rays_total / t_total / 1e6
-    what = ("the reference's own renderer.py / network.py (bytecode, oracle/_ref/pyc) + C restatement of its two CUDA-only encoder "
+    what = ("the reference's own renderer.py / network.py (bytecode, oracle/_ref/bytecode) + C restatement of its two CUDA-only encoder "
             "kernels" if kind == "reference" else "oracle port of the reference's renderer / network + C restatement of its encoder kernels")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "Mrays/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps),

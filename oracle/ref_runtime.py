@@ -1,6 +1,6 @@
 """Run the REFERENCE ITSELF from the staged build outputs under oracle/_ref.  TEST INFRASTRUCTURE ONLY.
 
-    oracle/_ref/pyc/...           the reference's unmodified Python, byte-compiled by oracle/stage_ref.py
+    oracle/_ref/bytecode/...      the reference's unmodified Python, byte-compiled by oracle/stage_ref.py
     oracle/_ref/_gridencoder.so   the reference's unmodified CUDA kernels, compiled by oracle/build_ref.py
     oracle/_ref/_shencoder.so, _freqencoder.so
 
@@ -18,18 +18,46 @@ Only tests/ and bench.py's reference legs import this module.
 """
 import contextlib
 import importlib
+import importlib.abc
+import importlib.machinery
+import importlib.util
 import os
 import sys
 import types
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REFDIR = os.path.join(HERE, "_ref")
-PYC = os.path.join(REFDIR, "pyc")
+PYC = os.path.join(REFDIR, "bytecode")
+EXT = ".bin"
+
+
+class _RefFinder(importlib.abc.MetaPathFinder):
+    """Resolves the reference's module names to the staged bytecode files (first on sys.meta_path while `env()` is active)."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if fullname.split(".")[0] not in ("nerf", "encoding", "activation", "gridencoder", "shencoder", "freqencoder"):
+            return None
+        rel = os.path.join(PYC, *fullname.split("."))
+        init = os.path.join(rel, "__init__" + EXT)
+        if os.path.exists(init):
+            return importlib.util.spec_from_file_location(fullname, init, loader=importlib.machinery.SourcelessFileLoader(fullname, init),
+                                                          submodule_search_locations=[rel])
+        if os.path.exists(rel + EXT):
+            return importlib.util.spec_from_file_location(fullname, rel + EXT,
+                                                          loader=importlib.machinery.SourcelessFileLoader(fullname, rel + EXT))
+        if os.path.isdir(rel):       # `nerf` has no __init__.py in the reference: a namespace package
+            spec = importlib.machinery.ModuleSpec(fullname, None, is_package=True)
+            spec.submodule_search_locations = [rel]
+            return spec
+        return None
+
+
+_FINDER = _RefFinder()
 
 _REF_ROOTS = ("nerf", "encoding", "activation", "gridencoder", "shencoder", "freqencoder", "_gridencoder", "_shencoder",
               "_freqencoder", "mcubes", "trimesh", "torch_efficient_distloss", "torch_ema", "imageio", "matplotlib", "wandb",
               "tensorboardX")
-_state = {"backend": None, "mods": {}, "depth": 0, "orig": None}
+_state = {"active": None, "depth": 0, "orig": None, "mods": {}}     # mods: backend -> the reference module set loaded with it
 
 
 def _is_ref_name(name):
@@ -38,7 +66,7 @@ def _is_ref_name(name):
 
 def available(backend="cuda"):
     """True when the staged build outputs this backend needs are present."""
-    ok = os.path.exists(os.path.join(PYC, "nerf", "renderer.pyc")) and os.path.exists(os.path.join(PYC, "encoding.pyc"))
+    ok = os.path.exists(os.path.join(PYC, "nerf", "renderer" + EXT)) and os.path.exists(os.path.join(PYC, "encoding" + EXT))
     if backend == "cuda":
         ok = ok and all(os.path.exists(os.path.join(REFDIR, n + ".so")) for n in ("_gridencoder", "_shencoder"))
     return ok
@@ -135,33 +163,36 @@ def _stub_modules(backend):
 
 @contextlib.contextmanager
 def env(backend="cuda"):
-    """Inside: `import nerf.renderer`, `encoding`, `gridencoder`, ... resolve to the REFERENCE (oracle/_ref/pyc) and
+    """Inside: `import nerf.renderer`, `encoding`, `gridencoder`, ... resolve to the REFERENCE (oracle/_ref/bytecode) and
     `_gridencoder` / `_shencoder` to the chosen backend.  Outside: to whatever they resolved to before (this repo's shims).
-    Re-entrant; one backend per process (grid.py binds `_backend` at import time)."""
-    if _state["backend"] not in (None, backend):
-        raise RuntimeError(f"oracle.ref_runtime: backend '{_state['backend']}' is already loaded in this process")
+    Re-entrant for the same backend; each backend keeps its own set of reference modules (grid.py binds `_backend` at import
+    time), so the "cuda" and the "cpu" reference can live in one process, one at a time."""
+    if _state["active"] not in (None, backend):
+        raise RuntimeError(f"oracle.ref_runtime: env('{_state['active']}') is active; leave it before entering env('{backend}')")
     if not available(backend):
         raise RuntimeError("oracle.ref_runtime: oracle/_ref is not staged (python oracle/stage_ref.py; python oracle/build_ref.py)")
     _state["depth"] += 1
     if _state["depth"] == 1:
-        if _state["backend"] is None:
-            _state["backend"] = backend
-            _state["mods"] = _stub_modules(backend)
+        _state["active"] = backend
+        if backend not in _state["mods"]:
+            _state["mods"][backend] = _stub_modules(backend)
         _state["orig"] = {k: sys.modules.pop(k) for k in list(sys.modules) if _is_ref_name(k)}
-        sys.modules.update(_state["mods"])
-        sys.path[:0] = [PYC, REFDIR]
+        sys.modules.update(_state["mods"][backend])
+        sys.meta_path.insert(0, _FINDER)
+        if backend == "cuda":
+            sys.path.insert(0, REFDIR)            # the compiled pybind modules _gridencoder / _shencoder / _freqencoder
     try:
         yield
     finally:
         _state["depth"] -= 1
         if _state["depth"] == 0:
-            _state["mods"] = {k: sys.modules.pop(k) for k in list(sys.modules) if _is_ref_name(k)}
+            _state["mods"][backend] = {k: sys.modules.pop(k) for k in list(sys.modules) if _is_ref_name(k)}
             sys.modules.update(_state["orig"])
-            _state["orig"] = None
-            for p in (PYC, REFDIR):
-                if p in sys.path:
-                    sys.path.remove(p)
-            importlib.invalidate_caches()
+            _state["orig"], _state["active"] = None, None
+            if _FINDER in sys.meta_path:
+                sys.meta_path.remove(_FINDER)
+            if REFDIR in sys.path:
+                sys.path.remove(REFDIR)
 
 
 def modules(backend="cuda"):

@@ -14,7 +14,15 @@ verbatim by oracle/build_ref.py), fp32, TF32 off.  Compared on identical weights
 Tolerance: |cand - ref| <= 1e-3 * max(|ref|, floor), floor = 1e-3 for image / depth / weights_sum; for the signed
 feature vectors (samvit, instance_mask_logits) floor = max(1e-3, 0.1 * rms(ref)) -- justified by
 `test_reference_gpu_vs_cpu_oracle_floors`, which measures how the reference's own fp32 GPU path scores against the fp32 CPU
-oracle at both floors.  The measured margins are written to gpurun_out/ref_gpu_parity.json.
+oracle at both floors (measured on B200: the reference's GPU samvit is 1.7e-2 away from the CPU oracle at the strict floor, i.e.
+the strict floor is not a property of the algorithm in fp32; 2.9e-4 at the rms floor).
+
+Arbitration for the 256-d SAM feature: the 5-layer MLP + LayerNorm amplifies a one-ulp difference in a resampled bin, so
+on a whole frame (164 M values) two fp32 evaluations of the reference algorithm disagree beyond 1e-3 on a handful of rays --
+measured: on the worst ray of pose 11 the reference's GPU path is 2.6e-2 away from the CPU oracle while the candidate is 2e-4 away
+from it; on another ray both GPU paths agree to 8e-5 and sit 1.4e-3 from the CPU oracle (tools/diag_outlier.py).  For such rays
+(at most 2e-5 of the frame) the candidate must agree within tolerance with at least ONE of the two references: the reference's
+GPU path or the CPU oracle.  The measured margins are written to gpurun_out/ref_gpu_parity.json.
 """
 import json
 import os
@@ -87,7 +95,31 @@ def _rms_floor(ref):
     return max(1e-3, 0.1 * float(ref.double().pow(2).mean().sqrt()))
 
 
-def _check(name, cand_out, ref_out, signed=()):
+def _arbitrate(key, cv, rv, floor, arb):
+    """Rays whose `key` deviates from the reference GPU beyond 1e-3 (at `floor`): re-evaluated with the CPU oracle; each must
+    agree with the oracle instead.  Returns (number of such rays, worst candidate-vs-oracle error on them, worst error of the other rays)."""
+    import bench
+    from oracle import render_oracle
+    wl, cand, ro, rd, kw = arb
+    n = ro.shape[0]
+    a, b = cv.reshape(n, -1).double(), rv.reshape(n, -1).double()
+    per_ray = ((a - b).abs() / b.abs().clamp(min=floor)).amax(dim=1)
+    bad = torch.nonzero(per_ray > 1e-3).reshape(-1)
+    good_max = float(per_ray[per_ray <= 1e-3].max()) if bool((per_ray <= 1e-3).any()) else 0.0
+    if bad.numel() == 0:
+        return 0, 0.0, good_max
+    assert bad.numel() <= max(2, int(2e-5 * n)), f"{key}: {bad.numel()} rays deviate from the reference GPU beyond tolerance"
+    params = {k: v.detach().cpu() for k, v in cand.state_dict().items()}
+    okw = dict(kw)
+    if "return_feats" in okw:
+        okw.update(H=1, W=int(bad.numel()))
+    cpu, _ = render_oracle.run(params, render_oracle.default_specs(2), bench.default_opt(wl), ro[bad].cpu(), rd[bad].cpu(), bg_color=1, **okw)
+    c = cpu[key].reshape(bad.numel(), -1).double().to(a.device)
+    worst = float(((a[bad] - c).abs() / c.abs().clamp(min=floor)).max())
+    return int(bad.numel()), worst, good_max
+
+
+def _check(name, cand_out, ref_out, signed=(), arb=None):
     stats = {}
     for k, rv in ref_out.items():
         if not torch.is_tensor(rv):
@@ -95,7 +127,14 @@ def _check(name, cand_out, ref_out, signed=()):
         cv = cand_out[k].reshape(rv.shape)
         stats[k] = _errors(cv, rv, 1e-3)
         if k in signed:
-            stats[k + "@rms_floor"] = _errors(cv, rv, _rms_floor(rv))
+            floor = _rms_floor(rv)
+            stats[k + "@rms_floor"] = _errors(cv, rv, floor)
+            if arb is not None and stats[k + "@rms_floor"]["max"] > 1e-3:
+                n_bad, worst, good_max = _arbitrate(k, cv, rv, floor, arb)
+                stats[k + "@rms_floor"].update(rays_arbitrated_by_cpu_oracle=n_bad, max_vs_cpu_oracle_on_them=worst,
+                                               max_before_arbitration=stats[k + "@rms_floor"]["max"])
+                assert worst <= 1e-3, f"{name}/{k}: {n_bad} rays deviate from the reference GPU AND from the CPU oracle ({worst:.3e})"
+                stats[k + "@rms_floor"]["max"] = max(good_max, worst)
     _record(name, stats)
     for k, s in stats.items():
         if k in signed:
@@ -160,7 +199,7 @@ def test_sam_full_frame_vs_reference_gpu():
         want = R.render_features_by_rows(ref, ro, rd, W, rows_per_call=5, perturb=False, bg_color=1)
         got = cand.render(ro, rd, staged=False, perturb=False, bg_color=1, return_feats=1, H=H, W=W, image_width=W)
     assert want["samvit"].shape == (H * W, 256) and got["samvit"].shape == (H, W, 256)
-    stats = _check("config3_sam_frame", got, want, signed=("samvit",))
+    stats = _check("config3_sam_frame", got, want, signed=("samvit",), arb=("sam", cand, ro, rd, dict(return_feats=1)))
     assert stats["samvit@rms_floor"]["max"] <= 1e-3, stats["samvit@rms_floor"]
 
 

@@ -1,6 +1,6 @@
 """GPU: the B-model boundary proven with the REFERENCE'S OWN CALLER.
 
-The reference's unmodified `nerf/trainer.py::Trainer` (oracle/_ref/pyc) is constructed over this repo's drop-in
+The reference's unmodified `nerf/trainer.py::Trainer` (oracle/_ref/bytecode) is constructed over this repo's drop-in
 `NeRFNetwork` and over the reference's own `NeRFNetwork` (reference kernels, oracle/_ref/*.so) with identical weights; its
 `test_step` (:692), `eval_step` (:570), one rgb `train_step` (:336) + `post_train_step` (TV / weight-decay hooks, :558) and
 one object-stage `train_step` after main.py's name-based freezing (main.py:249-256) must give the same numbers on both, and
@@ -146,6 +146,7 @@ def test_object_stage_freezing_train_step_and_checkpoint_roundtrip():
         with R.env("cuda"):
             for name, model in models.items():
                 tr = TH.make_trainer(R, "cuda", model, opt_obj, os.path.join(ws, name))
+                torch.manual_seed(5)           # the TV regulariser draws its 10^6 sample points with torch.rand (grid.py:183)
                 model.train()
                 tr.global_step += 1
                 tr.optimizer.zero_grad()

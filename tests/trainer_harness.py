@@ -1,4 +1,4 @@
-"""Harness that drives the REFERENCE'S OWN `nerf/trainer.py::Trainer` (byte-compiled under oracle/_ref/pyc, unmodified) on top
+"""Harness that drives the REFERENCE'S OWN `nerf/trainer.py::Trainer` (byte-compiled under oracle/_ref/bytecode, unmodified) on top
 of a model -- this repo's drop-in `NeRFNetwork` in the GPU tests, the reference's own model in the CPU dry run that checks the
 harness itself.  The trainer is the B-model caller of SURVEY.md 8b: `train_step` (:336), `eval_step` (:570), `test_step`
 (:692), `post_train_step` (:558), plus main.py's optimizer wiring (`model.get_params`, main.py:283) and name-based freezing
