@@ -352,6 +352,8 @@ def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, ste
             dist.barrier()
         torch.cuda.synchronize()
         ms = torch.tensor([sum(a.elapsed_time(b) for a, b in evs)], device=dev, dtype=torch.float64)
+        if os.environ.get("SANERF_BENCH_DEBUG"):
+            print(f"[rank {rank}] {wl} step ms: " + " ".join(f"{a.elapsed_time(b):.2f}" for a, b in evs), file=sys.stderr, flush=True)
         if world > 1:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item()), _lib.launch_counter["n"] - n0

@@ -246,6 +246,15 @@ int sanerf_mask_head(const float *records, const float *weights, const sanerf_gr
 size_t sanerf_samvit_mlp_workspace_bytes(void);
 int sanerf_samvit_mlp(const float *sam_in, const float *const *w, const float *const *b, const float *ln_w, const float *ln_b,
                       uint32_t n_rays, void *workspace, float *out, sanerf_stream_t stream);
+/* Same with the output layout chosen by the caller: out_nchw = 0 -> [n_rays,256] (as above); 1 -> channel-major [256,n_rays], i.e.
+ * the [1,256,H,W] tensor the reference's consumer builds with reshape + permute + contiguous (nerf/trainer.py:540-541), written
+ * directly by the head's epilogue. */
+int sanerf_samvit_mlp_layout(const float *sam_in, const float *const *w, const float *const *b, const float *ln_w, const float *ln_b,
+                             uint32_t n_rays, void *workspace, float *out, uint32_t out_nchw, sanerf_stream_t stream);
+/* Fused permute + bilinear resize of a feature frame (nerf/trainer.py:540-546: NHWC -> NCHW, then F.interpolate(mode='bilinear',
+ * align_corners=False) to (Ho,Wo)): in_hwc [h,w,C] -> out_chw [C,Ho,Wo], reading only the taps needed. */
+int sanerf_feature_resize_nchw(const float *in_hwc, uint32_t h, uint32_t w, uint32_t C, uint32_t Ho, uint32_t Wo, float *out_chw,
+                               sanerf_stream_t stream);
 
 /* Validation entry point for the tcgen05 (5th-gen tensor core) MLP path that the fused render uses for grid_mlp
  * (nerf/network.py:9-29 `MLP`, bias-free, ReLU between layers): out[M,16] = relu(relu(x W0^T) W1^T) W2^T with

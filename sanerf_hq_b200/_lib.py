@@ -61,6 +61,8 @@ PROTOTYPES = {
     "sanerf_mask_head": [_vp, _vp, ctypes.POINTER(GridT), _vp, _vp, _vp, _u32, _u32, _vp, _vp, _vp],
     "sanerf_samvit_mlp_workspace_bytes": [],
     "sanerf_samvit_mlp": [_vp, _vp * 5, _vp * 5, _vp, _vp, _u32, _vp, _vp, _vp],
+    "sanerf_samvit_mlp_layout": [_vp, _vp * 5, _vp * 5, _vp, _vp, _u32, _vp, _vp, _u32, _vp],
+    "sanerf_feature_resize_nchw": [_vp, _u32, _u32, _u32, _u32, _u32, _vp, _vp],
     "sanerf_peer_alloc": [ctypes.c_size_t, ctypes.POINTER(_vp)],
     "sanerf_peer_free": [_vp],
     "sanerf_peer_export": [_vp, ctypes.c_char_p],

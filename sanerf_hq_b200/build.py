@@ -13,7 +13,10 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIBDIR = os.path.join(HERE, "lib")
+# SANERF_LIB_VARIANT=<name> builds / loads sanerf_hq_b200/lib_<name>/ instead (kernel experiments: several variants of the
+# library, compiled with different SANERF_NVCC_FLAGS, side by side in one gpurun snapshot)
+_VARIANT = os.environ.get("SANERF_LIB_VARIANT", "")
+LIBDIR = os.path.join(HERE, "lib_" + _VARIANT if _VARIANT else "lib")
 SO = os.path.join(LIBDIR, "libsanerf_b200.so")
 SOURCES = ["grid_encode.cu", "sh_encode.cu", "freq_encode.cu", "render.cu", "mlp_tc.cu", "heads.cu", "peer.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc.cuh"), os.path.join(CSRC, "grid_dev.cuh"), os.path.join(os.path.dirname(HERE), "include", "sanerf_b200.h")]

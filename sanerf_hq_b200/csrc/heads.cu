@@ -125,6 +125,9 @@ __device__ __forceinline__ void issue_ksteps(uint32_t d_tmem, uint32_t a_col, ui
 // bf16 hi/lo split) IN PLACE to the first half of the next layer's A operand while the tensor cores are busy with half 1;
 // the next layer then starts on the K range that is ready while part 1 converts the second half.  The tensor pipe only waits
 // for an epilogue at the end of a tile.  TMEM: two 256-column regions that swap roles (A / D) from layer to layer.
+// Measured and rejected: x-paired producer gathers (8 lanes per sample, the x-neighbours of a corner fetched by adjacent lanes:
+// 1/3 fewer L1 line lookups, 40 % more producer instructions): 13.1 -> 15.7 ms per frame -- the producers are issue-bound as
+// much as L1-bound.  (The same pairing pays in the render kernel's final stage, whose C=2 gathers are L1-bound: render.cu.)
 #ifndef SANERF_MASK_PRODUCER_WARPS
 #define SANERF_MASK_PRODUCER_WARPS 16
 #endif
@@ -431,7 +434,8 @@ __device__ __forceinline__ void issue_chunk_rt(uint32_t d_tmem, uint32_t a_col, 
 __global__ void __launch_bounds__(kHeadThreads, 1)
     samvit_mlp_kernel(const float* __restrict__ sam_in, const __nv_bfloat16* __restrict__ img, const float* __restrict__ b0,
                       const float* __restrict__ b1, const float* __restrict__ b2, const float* __restrict__ b3, const float* __restrict__ b4,
-                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ out, uint32_t n_tiles, uint32_t n_rays) {
+                      const float* __restrict__ ln_w, const float* __restrict__ ln_b, float* __restrict__ out, uint32_t n_tiles, uint32_t n_rays,
+                      uint32_t out_nchw) {
     extern __shared__ __align__(128) uint8_t smem[];   // [2 stages x 64 KB][input tile 128 x 163 fp32]
     __shared__ __align__(8) uint64_t bar_full[2], bar_free[2], bar_done, bar_in;
     __shared__ uint32_t tmem_base_s;
@@ -614,7 +618,14 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
                             const int c = grp * 16 + i + j;
                             y[j] = (__uint_as_float(t[i + j]) + __ldg(b4 + c) - mean) * rstd * __ldg(ln_w + c) + __ldg(ln_b + c);
                         }
-                        *reinterpret_cast<float4*>(dst + i) = make_float4(y[0], y[1], y[2], y[3]);
+                        if (!out_nchw) {
+                            *reinterpret_cast<float4*>(dst + i) = make_float4(y[0], y[1], y[2], y[3]);
+                        } else {
+                            // channel-major [256][n_rays] = the [1,256,H,W] tensor of trainer.py:540-541 (reshape + permute +
+                            // contiguous) written directly: the 32 lanes of a warp are 32 consecutive rays -> coalesced rows
+#pragma unroll
+                            for (int j = 0; j < 4; j++) out[(size_t)(grp * 16 + i + j) * n_rays + ray] = y[j];
+                        }
                     }
                 }
             }
@@ -623,6 +634,40 @@ __global__ void __launch_bounds__(kHeadThreads, 1)
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tm, 512);
+}
+
+// Output consumer of the feature frame (nerf/trainer.py:540-546): `samvit.reshape(1,h,w,C).permute(0,3,1,2)
+// .contiguous()` followed by `F.interpolate(..., (Ho,Wo), mode='bilinear')` (align_corners=False) in ONE pass over the taps that
+// are actually needed: out[c,i,j] = bilinear blend of in[y0..y1, x0..x1, c], source index max((dst + 0.5) * in/out - 0.5, 0) like
+// ATen's upsample_bilinear2d.  One block = 32 output columns of one output row; threads = channels on the (coalesced) read side,
+// a shared-memory transpose makes the [C][Ho][Wo] writes coalesced too.
+__global__ void __launch_bounds__(256) feature_resize_nchw_kernel(const float* __restrict__ in, uint32_t h, uint32_t w, uint32_t C, uint32_t Ho,
+                                                                  uint32_t Wo, float* __restrict__ out) {
+    __shared__ float tile[256][33];
+    const uint32_t i = blockIdx.y, j0 = blockIdx.x * 32;
+    const float rh = (float)h / (float)Ho, rw = (float)w / (float)Wo;
+    const float ys = fmaxf(rh * ((float)i + 0.5f) - 0.5f, 0.f);
+    const uint32_t y0 = (uint32_t)ys, yp = y0 < h - 1 ? 1u : 0u;
+    const float ly1 = ys - (float)y0, ly0 = 1.f - ly1;
+    for (uint32_t c0 = 0; c0 < C; c0 += 256) {
+        const uint32_t c = c0 + threadIdx.x;
+        for (uint32_t jj = 0; jj < 32 && j0 + jj < Wo; jj++) {
+            const float xs = fmaxf(rw * ((float)(j0 + jj) + 0.5f) - 0.5f, 0.f);
+            const uint32_t x0 = (uint32_t)xs, xp = x0 < w - 1 ? 1u : 0u;
+            const float lx1 = xs - (float)x0, lx0 = 1.f - lx1;
+            if (c < C) {
+                const float* p = in + ((size_t)y0 * w + x0) * C + c;
+                const float v00 = __ldg(p), v01 = __ldg(p + (size_t)xp * C), v10 = __ldg(p + (size_t)yp * w * C),
+                            v11 = __ldg(p + ((size_t)yp * w + xp) * C);
+                tile[threadIdx.x][jj] = ly0 * (lx0 * v00 + lx1 * v01) + ly1 * (lx0 * v10 + lx1 * v11);
+            }
+        }
+        __syncthreads();
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (uint32_t cc = warp; cc < 256 && c0 + cc < C; cc += 8)
+            if (j0 + lane < Wo) out[((size_t)(c0 + cc) * Ho + i) * Wo + j0 + lane] = tile[cc][lane];
+        __syncthreads();
+    }
 }
 
 static size_t sam_build_chunks(SamChunk* out) {
@@ -693,6 +738,11 @@ size_t sanerf_samvit_mlp_workspace_bytes(void) {
 
 int sanerf_samvit_mlp(const float* sam_in, const float* const* w, const float* const* b, const float* ln_w, const float* ln_b, uint32_t n_rays,
                       void* workspace, float* out, sanerf_stream_t stream) {
+    return sanerf_samvit_mlp_layout(sam_in, w, b, ln_w, ln_b, n_rays, workspace, out, 0, stream);
+}
+
+int sanerf_samvit_mlp_layout(const float* sam_in, const float* const* w, const float* const* b, const float* ln_w, const float* ln_b,
+                             uint32_t n_rays, void* workspace, float* out, uint32_t out_nchw, sanerf_stream_t stream) {
     if (n_rays == 0) return 0;
     if (!sam_in || !w || !b || !ln_w || !ln_b || !workspace || !out) return SANERF_E_NULL;
     for (int i = 0; i < 5; i++)
@@ -714,7 +764,17 @@ int sanerf_samvit_mlp(const float* sam_in, const float* const* w, const float* c
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const uint32_t n_tiles = div_up(n_rays, 128u);
     samvit_mlp_kernel<<<n_tiles < (uint32_t)sms ? n_tiles : (uint32_t)sms, kHeadThreads, smem, st>>>(
-        sam_in, img, b[0], b[1], b[2], b[3], b[4], ln_w, ln_b, out, n_tiles, n_rays);
+        sam_in, img, b[0], b[1], b[2], b[3], b[4], ln_w, ln_b, out, n_tiles, n_rays, out_nchw);
+    return check_launch();
+}
+
+int sanerf_feature_resize_nchw(const float* in_hwc, uint32_t h, uint32_t w, uint32_t C, uint32_t Ho, uint32_t Wo, float* out_chw,
+                               sanerf_stream_t stream) {
+    if (!in_hwc || !out_chw) return SANERF_E_NULL;
+    if (h == 0 || w == 0 || C == 0 || Ho == 0 || Wo == 0) return 0;
+    if (C > 1024) return SANERF_E_CONFIG;
+    const dim3 grid(div_up(Wo, 32u), Ho);
+    feature_resize_nchw_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(in_hwc, h, w, C, Ho, Wo, out_chw);
     return check_launch();
 }
 

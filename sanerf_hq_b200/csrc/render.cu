@@ -36,6 +36,9 @@ namespace sanerf {
 #endif
 constexpr int kWarps = SANERF_RENDER_WARPS;   // warps (= rays in flight) per CTA; 4 warps = one tensor-core group
 constexpr int kGroups = kWarps / 4;
+#ifndef SANERF_S2_XPAIR
+#define SANERF_S2_XPAIR 1   // 1: x-paired lanes in the final-stage gathers (see pair_issue); 800x800 RGB frame 11.31 -> 11.04 ms
+#endif
 #ifndef SANERF_PROP_DEPTH
 #define SANERF_PROP_DEPTH 1   // levels of loads in flight per chunk in the proposal gathers (1: 11.90 ms, 2: 11.99 ms)
 #endif
@@ -180,6 +183,58 @@ __device__ __forceinline__ void level_finish(const LevelLoads& o, float& o0, flo
         float ww = (i & 1) ? o.f[0] : 1 - o.f[0];
         ww *= (i & 2) ? o.f[1] : 1 - o.f[1];
         ww *= (i & 4) ? o.f[2] : 1 - o.f[2];
+        a0 = __fmaf_rn(ww, o.v[i].x, a0);
+        a1 = __fmaf_rn(ww, o.v[i].y, a1);
+    }
+    o0 = a0;
+    o1 = a1;
+}
+
+// ---- x-paired gathers (SANERF_S2_XPAIR) ----------------------------------------------------------------------------------
+// Two adjacent lanes share one sample: the even lane fetches the four corners with x = x0, the odd lane those with x = x0+1.
+// The two x-neighbours of a (y,z) corner pair are adjacent table rows on the dense levels and on the hashed levels whenever x0
+// is even (the hash only XORs x in), i.e. they sit in the same 128-byte line, and both lanes are served by ONE L1 line lookup
+// instead of two lookups from two instructions.  A request then touches 16 x (4..8) lines for 16 samples instead of 32 lines
+// for 32 samples and 1/8 of their corners: ~35 % fewer L1 line lookups for ~45 more instructions per level.
+struct PairLoads {
+    float2 v[4];
+    float f[3];
+};
+
+__device__ __forceinline__ void pair_issue(const GridDev& g, int l, const float (&x)[3], int xside, PairLoads& o) {
+    const uint32_t res = g.res[l];
+    const uint32_t hmask = g.hmask[l];
+    const float2* __restrict__ rows = reinterpret_cast<const float2*>(g.base[l]);
+    const float resf = g.resf[l], top = g.topf[l];
+    uint32_t b0[3], b1[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        float pos = fminf(fmaxf(__fmaf_rn(x[d], resf, -0.5f), 0.0f), top);
+        floor_split(pos, b0[d], o.f[d]);
+        b1[d] = min(b0[d] + 1, res - 1);
+    }
+    const uint32_t bx = xside ? b1[0] : b0[0];
+    if (hmask == 0) {
+        const uint32_t y0 = b0[1] * res, y1 = b1[1] * res, z0 = b0[2] * res * res, z1 = b1[2] * res * res;
+#pragma unroll
+        for (int i = 0; i < 4; i++) o.v[i] = __ldg(rows + (bx + ((i & 1) ? y1 : y0) + ((i & 2) ? z1 : z0)));
+    } else {
+        const uint32_t xm = bx & hmask;
+        const uint32_t y0 = (b0[1] * 2654435761u) & hmask, y1 = (b1[1] * 2654435761u) & hmask;
+        const uint32_t z0 = (b0[2] * 805459861u) & hmask, z1 = (b1[2] * 805459861u) & hmask;
+#pragma unroll
+        for (int i = 0; i < 4; i++) o.v[i] = __ldg(rows + (xm ^ ((i & 1) ? y1 : y0) ^ ((i & 2) ? z1 : z0)));
+    }
+}
+
+// this lane's half of the trilinear blend (weights in the reference's product order (wx*wy)*wz, gridencoder.cu:170-195)
+__device__ __forceinline__ void pair_finish(const PairLoads& o, int xside, float& o0, float& o1) {
+    const float wx = xside ? o.f[0] : 1 - o.f[0];
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float ww = wx * ((i & 1) ? o.f[1] : 1 - o.f[1]);
+        ww *= (i & 2) ? o.f[2] : 1 - o.f[2];
         a0 = __fmaf_rn(ww, o.v[i].x, a0);
         a1 = __fmaf_rn(ww, o.v[i].y, a1);
     }
@@ -505,6 +560,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     // re-renders the last ray and skips the stores.  Rays are dealt to the CTAs round-robin, 16 at a time: at any moment the
     // whole GPU works on the same ~3 image rows, which keeps the cells they share hot in L2 (measured: giving each CTA one
     // contiguous block of rays instead costs +2 % on the RGB frame and +35 % on the SAM frame, whose 160 MiB table overflows L2)
+    // (measured and without effect: letting a CTA take runs of 2 / 4 / 8 neighbouring tiles so that the next tile finds its
+    // neighbours' table lines in L1: 11.06 / 11.09 / 11.13 / 11.12 ms)
     for (uint32_t base = blockIdx.x * kWarps; base < p.N; base += total_warps) {
         bool active = base + warp < p.N;
         uint32_t ray = active ? base + warp : p.N - 1;
@@ -583,6 +640,56 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             constexpr int GKP = S::GKP;                  // K of the first layer padded to 16
             static_assert(GL % 4 == 0, "grid levels come in blocks of 4");
             tmem_begin();
+#if SANERF_S2_XPAIR
+            {
+                // pass q (0, 1): lanes (2k, 2k+1) gather sample 16 q + k; units (level, pass) are software-pipelined four deep
+                const int xside = lane & 1;
+                float px[2][3];
+#pragma unroll
+                for (int q = 0; q < 2; q++)
+#pragma unroll
+                    for (int d = 0; d < 3; d++) px[q][d] = __shfl_sync(kFull, x01[d], 16 * q + (lane >> 1));
+                const int src = 2 * (lane & 15) + (lane >> 4);     // where this lane's own sample ends up (see below)
+                PairLoads pb[4];                                   // ring: unit u = 2 * level + pass lives in pb[u % 4]
+                pair_issue(p.grid, 0, px[0], xside, pb[0]);
+                pair_issue(p.grid, 0, px[1], xside, pb[1]);
+                pair_issue(p.grid, 1, px[0], xside, pb[2]);
+                pair_issue(p.grid, 1, px[1], xside, pb[3]);
+#pragma unroll 1
+                for (int lb = 0; lb < GKP / 8; lb++) {
+                    uint32_t hi[4], lo[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        const int l = 4 * lb + j;
+                        float o0 = 0.f, o1 = 0.f;
+                        if (l < GL) {                  // uniform
+                            float a0, a1, c0, c1;
+                            pair_finish(pb[(2 * j) % 4], xside, a0, a1);
+                            if (l + 2 < GL) pair_issue(p.grid, l + 2, px[0], xside, pb[(2 * j) % 4]);
+                            pair_finish(pb[(2 * j + 1) % 4], xside, c0, c1);
+                            if (l + 2 < GL) pair_issue(p.grid, l + 2, px[1], xside, pb[(2 * j + 1) % 4]);
+                            // both halves of a sample -> both lanes of its pair; then the even lane of pair k offers sample k
+                            // (pass 0) and the odd lane sample 16 + k (pass 1), and every lane fetches its own sample
+                            a0 += __shfl_xor_sync(kFull, a0, 1);
+                            a1 += __shfl_xor_sync(kFull, a1, 1);
+                            c0 += __shfl_xor_sync(kFull, c0, 1);
+                            c1 += __shfl_xor_sync(kFull, c1, 1);
+                            o0 = __shfl_sync(kFull, xside ? c0 : a0, src);
+                            o1 = __shfl_sync(kFull, xside ? c1 : a1, src);
+                        }
+                        o0 = inside ? o0 : 0.f;
+                        o1 = inside ? o1 : 0.f;
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(o0, o1);
+                        const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+                        const __nv_bfloat162 lw = __floats2bfloat162_rn(o0 - __uint_as_float(hb << 16), o1 - __uint_as_float(hb & 0xffff0000u));
+                        hi[j] = hb;
+                        lo[j] = *reinterpret_cast<const uint32_t*>(&lw);
+                    }
+                    tc::tmem_st4(grp.a_rw + 4 * lb, hi);
+                    tc::tmem_st4(grp.a_rw + GKP / 2 + 4 * lb, lo);
+                }
+            }
+#else
             {
                 LevelLoads buf0, buf1;             // levels 4*lb and 4*lb+1 are in flight at the top of each iteration
                 level_issue(p.grid, 0, x01, buf0);
@@ -616,6 +723,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                     tc::tmem_st4(grp.a_rw + GKP / 2 + 4 * lb, lo);
                 }
             }
+#endif
             {
                 const uint32_t d_mma = grp.d_mma, a_mma = grp.a_mma;
                 const __nv_bfloat16* w0 = reinterpret_cast<const __nv_bfloat16*>(sm + S::grid_w0);

@@ -215,17 +215,23 @@ class NeRFRenderer(nn.Module):
         return self._run_fused(None, None, camera=camera, return_uint8=return_uint8, **kw)
 
     def run(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
-            return_feats=0, return_mask=0, H=None, W=None, image_width=None, out=None, peer_out=None, max_ctas=0, **kwargs):
+            return_feats=0, return_mask=0, H=None, W=None, image_width=None, out=None, peer_out=None, max_ctas=0,
+            feature_layout=None, feature_size=None, **kwargs):
         """Not in the reference: `image_width` -- optional hint that the rays are a row-major image block of that width, which
         lets the fused kernel walk 4x4-pixel tiles (results are unchanged); `out` -- optional dict of preallocated result
         tensors (`image`, `depth`, `weights_sum`, `samvit`, `instance_mask_logits`) the kernels store into directly (used by
         parallel.FrameGather so that a rank's pixels land in its slot of the all-gather buffer without a copy); `peer_out` -- dict
         key -> list of raw device pointers (the other ranks' frame buffers in NVLink peer memory, at ray 0 of this call) that
-        the fused kernel additionally stores image / depth / weights_sum into; `max_ctas` -- cap on the persistent CTAs."""
+        the fused kernel additionally stores image / depth / weights_sum into; `max_ctas` -- cap on the persistent CTAs;
+        `feature_layout="nchw"` (+ optional `feature_size=(Ho, Wo)`) -- return the SAM feature frame as `samvit_nchw`
+        [1,256,Ho,Wo] instead of `samvit` [H,W,256]: the reshape / permute / contiguous / F.interpolate(bilinear) chain of the
+        reference's consumer (nerf/trainer.py:540-546) done by the head's epilogue (+ one fused resize pass when the size
+        changes) -- SURVEY.md 8f-3."""
         if self.opt.render_mesh:
             return {}  # the reference's mesh branch is commented out and returns an empty dict (renderer.py:386-498)
         kw = dict(bg_color=bg_color, perturb=perturb, cam_near_far=cam_near_far, update_proposal=update_proposal,
-                  return_feats=return_feats, return_mask=return_mask, H=H, W=W, image_width=image_width)
+                  return_feats=return_feats, return_mask=return_mask, H=H, W=W, image_width=image_width,
+                  feature_layout=feature_layout, feature_size=feature_size)
         if self._can_fuse(rays_o, kw):
             return self._run_fused(rays_o, rays_d, out=out, peer_out=peer_out, max_ctas=max_ctas, **kw)
         if peer_out:
@@ -335,7 +341,7 @@ class NeRFRenderer(nn.Module):
     @torch.no_grad()
     def _run_fused(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
                    return_feats=0, return_mask=0, H=None, W=None, taps=None, camera=None, return_uint8=False, image_width=None,
-                   out=None, peer_out=None, max_ctas=0, **kwargs):
+                   out=None, peer_out=None, max_ctas=0, feature_layout=None, feature_size=None, **kwargs):
         if camera is None:
             rays_o = rays_o.contiguous().float()
             rays_d = rays_d.contiguous().float()
@@ -432,7 +438,7 @@ class NeRFRenderer(nn.Module):
                 _lib.check(lib.sanerf_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "sanerf_render")
                 _lib.count_launch()
             if want_sam:
-                results["samvit"] = self._samvit_head(sam_in, out=out.get("samvit") if out else None).view(H, W, -1)
+                results.update(self._feature_results(sam_in, H, W, out, feature_layout, feature_size))
             return results
 
         # object head.  Default shapes: the fused kernel leaves an 18-float record (point, geo_feat) per sample and the
@@ -497,7 +503,7 @@ class NeRFRenderer(nn.Module):
                 point_masks = self.mask_mlp(mask_in[:n * 32 * width].view(n, 32, width))
                 logits[head:head + n] = torch.sum(wts.unsqueeze(-1) * point_masks, dim=-2)
         if want_sam:
-            results["samvit"] = self._samvit_head(sam_full, out=out.get("samvit") if out else None).view(H, W, -1)
+            results.update(self._feature_results(sam_full, H, W, out, feature_layout, feature_size))
         results["instance_mask_logits"] = logits
         return results
 
@@ -506,7 +512,30 @@ class NeRFRenderer(nn.Module):
         """[n, width] view of a buffer with whole tiles of `multiple` rows (the tensor-core heads read full tiles)."""
         return torch.empty(-(-max(n, 1) // multiple) * multiple, width, device=device)[:n]
 
-    def _samvit_head(self, f, out=None):
+    def _feature_results(self, f, H, W, out, layout, size):
+        """The SAM feature frame from the composited head inputs f [H*W,163]: `samvit` [H,W,256] like the reference
+        (renderer.py:371-374), or with layout "nchw" `samvit_nchw` [1,256,Ho,Wo] = permute + bilinear resize of it
+        (trainer.py:540-546) without materialising the intermediate tensors."""
+        if layout in (None, "nhwc"):
+            return {"samvit": self._samvit_head(f, out=out.get("samvit") if out else None).view(H, W, -1)}
+        if layout != "nchw":
+            raise ValueError(f"feature_layout must be None, 'nhwc' or 'nchw', not {layout!r}")
+        Ho, Wo = (int(v) for v in (size or (H, W)))
+        if (Ho, Wo) == (H, W):          # bilinear resampling to the same size is the identity: the head stores channel-major
+            return {"samvit_nchw": self._samvit_head(f, nchw=True).view(1, -1, H, W)}
+        nhwc = self._samvit_head(f)
+        if not nhwc.is_cuda:
+            return {"samvit_nchw": torch.nn.functional.interpolate(nhwc.view(1, H, W, -1).permute(0, 3, 1, 2).contiguous(), (Ho, Wo),
+                                                                   mode="bilinear")}
+        C = nhwc.shape[-1]
+        res = torch.empty(1, C, Ho, Wo, device=nhwc.device)
+        with torch.cuda.device(nhwc.device), _lib.timed("feature_resize_nchw_kernel"):
+            _lib.check(_lib.load().sanerf_feature_resize_nchw(_lib.ptr(nhwc), H, W, C, Ho, Wo, _lib.ptr(res), _lib.stream_ptr()),
+                       "sanerf_feature_resize_nchw")
+            _lib.count_launch()
+        return {"samvit_nchw": res}
+
+    def _samvit_head(self, f, out=None, nchw=False):
         """samvit_mlp (SkipConnMLP + LayerNorm, network.py:113-116) of the composited per-ray features f [n,163].
         No-grad CUDA input with the reference's shapes -> the tensor-core head (csrc/heads.cu); anything else -> nn.Modules.
         `out`: optional preallocated contiguous fp32 tensor with n*256 elements the head stores into."""
@@ -519,6 +548,8 @@ class NeRFRenderer(nn.Module):
               and f.untyped_storage().nbytes() - f.storage_offset() * 4 >= -(-f.shape[0] // 128) * 128 * 163 * 4)
         if not ok:
             res = self.samvit_mlp(f)
+            if nchw:
+                return res.t().contiguous()
             if out is not None:
                 out.view(-1, res.shape[-1]).copy_(res)
                 return out.view(-1, res.shape[-1])
@@ -535,11 +566,14 @@ class NeRFRenderer(nn.Module):
             raise RuntimeError(f"NeRFRenderer: out['samvit'] must be a contiguous fp32 tensor with {n} x 256 elements on {device}")
         else:
             out = out.view(n, 256)
+        if nchw:
+            out = out.view(256, n)
         wp = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in ws])
         bp = (ctypes.c_void_p * 5)(*[t.data_ptr() for t in bs])
         with torch.cuda.device(device), _lib.timed("samvit_mlp_kernel"):
-            _lib.check(lib.sanerf_samvit_mlp(_lib.ptr(f), wp, bp, _lib.ptr(ln.weight.detach()), _lib.ptr(ln.bias.detach()), n,
-                                             _lib.ptr(self._sam_ws), _lib.ptr(out), _lib.stream_ptr()), "sanerf_samvit_mlp")
+            _lib.check(lib.sanerf_samvit_mlp_layout(_lib.ptr(f), wp, bp, _lib.ptr(ln.weight.detach()), _lib.ptr(ln.bias.detach()), n,
+                                                    _lib.ptr(self._sam_ws), _lib.ptr(out), 1 if nchw else 0, _lib.stream_ptr()),
+                       "sanerf_samvit_mlp")
             _lib.count_launch(2)
         return out
 
@@ -547,7 +581,7 @@ class NeRFRenderer(nn.Module):
     # composed path (differentiable; also the perturb=True path)
     # ------------------------------------------------------------------------------------------
     def _run_composed(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
-                      return_feats=0, return_mask=0, H=None, W=None, **kwargs):
+                      return_feats=0, return_mask=0, H=None, W=None, feature_layout=None, feature_size=None, **kwargs):
         rays_o = rays_o.contiguous()
         rays_d = rays_d.contiguous()
         if not rays_o.is_cuda:
@@ -633,7 +667,13 @@ class NeRFRenderer(nn.Module):
                 f = torch.cat([f_sam, geo_sum, image, depth.unsqueeze(-1)], dim=-1)
             samvit = self._samvit_head(f)
             if return_feats > 0:
-                results["samvit"] = samvit.view(H, W, -1)
+                if feature_layout == "nchw":
+                    nchw = samvit.view(1, H, W, -1).permute(0, 3, 1, 2).contiguous()
+                    if feature_size is not None and tuple(feature_size) != (H, W):
+                        nchw = torch.nn.functional.interpolate(nchw, tuple(feature_size), mode="bilinear")
+                    results["samvit_nchw"] = nchw
+                else:
+                    results["samvit"] = samvit.view(H, W, -1)
 
         if return_mask > 0:
             if opt.mask_mlp_type == "default":

@@ -152,3 +152,37 @@ def test_samvit_head_matches_fp64(n_rays):
     assert torch.isfinite(got).all()
     assert (got - want).abs().max().item() < 2e-4 * float(want.abs().max())
     assert rel_err(got, want, floor=0.1 * float(want.pow(2).mean().sqrt())) < 1e-3
+
+
+def test_feature_frame_nchw_and_bilinear_resize_match_the_reference_consumer():
+    """`samvit.reshape(1,h,w,256).permute(0,3,1,2).contiguous()` + `F.interpolate(..., mode='bilinear')`
+    (nerf/trainer.py:540-546) produced by the head's epilogue (`feature_layout="nchw"`) and, when the size changes, one fused
+    permute + resize pass (`sanerf_feature_resize_nchw`)."""
+    import torch.nn.functional as F
+    from helpers import build_model, frame_rays, make_case
+    opt, params, specs = make_case(with_sam=True)
+    model = build_model(opt, params)
+    h, w = 24, 40
+    rays_o, rays_d = frame_rays(800, 800, pose_k=2, rows=(300, 300 + h), cols=(100, 100 + w))
+    rays_o, rays_d = rays_o.to(DEV), rays_d.to(DEV)
+    with torch.no_grad():
+        base = model.render(rays_o, rays_d, staged=False, perturb=False, return_feats=1, H=h, W=w)
+        nhwc = base["samvit"]
+        want = nhwc.reshape(1, h, w, 256).permute(0, 3, 1, 2).contiguous()
+        same = model.render(rays_o, rays_d, staged=False, perturb=False, return_feats=1, H=h, W=w, feature_layout="nchw")
+        assert "samvit" not in same and same["samvit_nchw"].shape == (1, 256, h, w)
+        assert torch.equal(same["samvit_nchw"], want)                              # the epilogue only changes where it stores
+        assert torch.equal(F.interpolate(want, (h, w), mode="bilinear"), want)     # same-size bilinear == identity
+        for size in ((64, 64), (7, 13), (48, 80)):                                 # up- and down-sampling, non-integer ratios
+            got = model.render(rays_o, rays_d, staged=False, perturb=False, return_feats=1, H=h, W=w, feature_layout="nchw",
+                               feature_size=size)["samvit_nchw"]
+            ref = F.interpolate(want, size, mode="bilinear")
+            assert got.shape == ref.shape
+            assert float((got - ref).abs().max()) <= 2e-6 * float(ref.abs().max()), size
+        # the raw operator on a random NHWC tensor with C not a multiple of 256
+        from sanerf_hq_b200 import _lib
+        x = torch.randn(17, 29, 300, device=DEV)
+        out = torch.empty(300, 64, 64, device=DEV)
+        _lib.check(_lib.load().sanerf_feature_resize_nchw(_lib.ptr(x), 17, 29, 300, 64, 64, _lib.ptr(out), _lib.stream_ptr()), "resize")
+        ref = F.interpolate(x.permute(2, 0, 1)[None].contiguous(), (64, 64), mode="bilinear")[0]
+        assert float((out - ref).abs().max()) <= 2e-6 * float(ref.abs().max())
