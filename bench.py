@@ -20,9 +20,10 @@ REFERENCE ITSELF on the same GPU (its unmodified Python, byte-compiled, on its o
 oracle/_ref) at max_ray_batch 4096 and 16384, same weights and poses, with the candidate's worst relative deviation from it;
 cpu_baseline = the reference's CPU path on the host cores over a bounded sample.
 
-Weak scaling at N GPUs: the frame grows to (800*N) x 800, rank r renders rows [800r, 800(r+1)) (model replicated, no data-path
-collective) and the composited frame is left on every rank through NVLink peer memory (sanerf_hq_b200/parallel.py: in-kernel
-peer stores + copy-engine pushes + one flag barrier; in-place NCCL all-gathers as the fallback) inside the timed region.
+Weak scaling at N GPUs: a step renders N views of the orbit, one 800x800 frame per GPU (model replicated, no data-path
+collective), and the N composited frames are left on every rank through NVLink peer memory (sanerf_hq_b200/parallel.py:
+in-kernel peer stores + copy-engine pushes + one flag barrier; in-place NCCL all-gathers as the fallback) inside the timed
+region.  (config5 is the strong-scaling counterpart: ONE frame, its rows sharded over the ranks.)
 
 --impl reference times the reference's own CPU implementation on the host cores: the reference's unmodified renderer / network
 Python (oracle/_ref/bytecode) over the C restatement of its two CUDA-only encoder kernels (the reference has no CPU encoder), all
@@ -234,7 +235,7 @@ def ref_gpu_baseline(wl, model, dev, H, W, poses, intr, cand_out0):
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         ref = R.build_network(default_opt(wl), model.state_dict(), device=dev)
-    rays = [get_rays(poses[k].to(dev), intr, H, W, device=dev) for k in range(3)]
+    rays = [tuple(t.to(dev) for t in get_rays(poses[k], intr, H, W)) for k in range(3)]      # the candidate's rays, bit for bit
     n = H * W
     out = {"what": "reference nerf/renderer.py + network.py (unmodified, byte-compiled) on the reference's CUDA kernels compiled verbatim "
                    "(oracle/_ref), fp32, TF32 off, same weights / poses / GPU", "unit": "Mrays/s"}
@@ -298,18 +299,22 @@ def result_spec(wl):
 
 
 def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, steps=None, warmup=None, tag=None):
-    """All numbers of one workload on this rank's `H x W` block (global frame `global_h` x W).  Returns a dict on rank 0."""
+    """All numbers of one workload on this rank's `H x W` rays.  Default (weak scaling): every rank renders its own view of the
+    orbit, H x W pixels; with `rows_of_rank` / `global_h` (strong scaling): rows `rows_of_rank` of ONE `global_h` x W frame.
+    Returns a dict on rank 0."""
     import torch.distributed as dist
     from sanerf_hq_b200 import _lib
     from sanerf_hq_b200.parallel import FrameGather
     from sanerf_hq_b200.rays import get_rays
     rank, world, dev = ctx["rank"], ctx["world"], ctx["dev"]
     steps, warmup = steps or args.steps, warmup or args.warmup
-    global_h = global_h or H * world
-    rows = rows_of_rank or (rank * H, (rank + 1) * H)
     from sanerf_hq_b200.rays import lego_intrinsics, orbit_pose
+    strong = rows_of_rank is not None
+    global_h = global_h if strong else H
+    rows = rows_of_rank if strong else (0, H)
     intr = lego_intrinsics(global_h, W)
-    poses = [orbit_pose(k, N_POSES) for k in range(N_POSES)]
+    # weak scaling: view (i * world + rank) of the orbit in step i; strong scaling: every rank works on view i
+    poses = [orbit_pose(k if strong else (k * world + rank) % N_POSES, N_POSES) for k in range(N_POSES)]
     model = build_model(wl, dev)
     n_local, n_total = H * W, H * W * world
     spec = result_spec(wl)
@@ -317,11 +322,13 @@ def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, ste
     kw = dict(return_mask=1) if wl == "mask" else (dict(return_feats=1) if wl == "sam" else {})
     groups = 1
     if wl == "sam" and world > 1:
-        groups = args.groups or 4
+        groups = args.groups or 8
     fg = FrameGather(n_local, spec, dev)
 
     n_res = min(N_POSES, steps + warmup)
-    host_rays = [tuple(t.pin_memory() for t in get_rays(poses[k], intr, global_h, W, rows=rows)) for k in range(n_res)]
+    # (strong scaling: the rows are sliced out of the full frame's rays so that every rank sees bit-identical ray values)
+    lo_ray, hi_ray = rows[0] * W, rows[1] * W
+    host_rays = [tuple(t[lo_ray:hi_ray].contiguous().pin_memory() for t in get_rays(poses[k], intr, global_h, W)) for k in range(n_res)]
     dev_rays = [(o.to(dev), d.to(dev)) for o, d in host_rays]
     hint = W if (n_local % (4 * W) == 0 and W % 4 == 0) else None
 
@@ -450,10 +457,13 @@ def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, ste
         achieved = BYTES_PER_RAY[wl] * n_local / (step_ms_kernels * 1e-3) / 1e9 if kernels else None
         res = {
             "value": value, "unit": "Mrays/s", "ms_per_step": ms_per_step, "steps": steps, "warmup": warmup,
-            "config": {"workload": f"{tag or wl} {H}x{W} per GPU (global frame {global_h}x{W}), hashgrid L=16 T=2^19, MLP 2x64, "
-                                   f"samples 128+64+32, one fused render launch per frame (reference: 4096 rays/batch)",
+            "config": {"workload": f"{tag or wl} {H}x{W} per GPU (" + (f"rows of one {global_h}x{W} frame" if strong else
+                                                                      f"{world} view(s) of {H}x{W} per step") +
+                                   "), hashgrid L=16 T=2^19, MLP 2x64, samples 128+64+32, one fused render launch per frame "
+                                   "(reference: 4096 rays/batch)",
                        "rays_per_step": n_total, "poses": n_res,
-                       "parallelism": f"ray-row sharding x{world}, transport {fg.transport}" + (f", {groups} row groups" if groups > 1 else ""),
+                       "parallelism": (f"rows of one frame sharded x{world}" if strong else f"one view per GPU x{world}") +
+                                      f", results gathered on every rank, transport {fg.transport}" + (f", {groups} row groups" if groups > 1 else ""),
                        "l2": "no flush" if flush is None else "L2 flushed between timed steps (256 MiB fill, outside the step events)",
                        "weights": "random init: seed-0 constructor, hash tables U(-1,1)"},
             # whole-path roofline by the SURVEY 8d convention (all kernels of the step), then the per-kernel list
@@ -504,7 +514,7 @@ def config5(args, ctx):
     if rank == 0:
         from sanerf_hq_b200.rays import get_rays, lego_intrinsics, orbit_pose
         with torch.no_grad():
-            ro, rd = get_rays(orbit_pose(0, N_POSES).to(dev), lego_intrinsics(Hg, Wg), Hg, Wg, device=dev)
+            ro, rd = (t.to(dev) for t in get_rays(orbit_pose(0, N_POSES), lego_intrinsics(Hg, Wg), Hg, Wg))   # as in measure()
             want = model.render(ro, rd, staged=False, perturb=False, return_feats=1, H=Hg, W=Wg, image_width=Wg)
             equal = {k: bool(torch.equal(got[k].reshape(-1), want[k].reshape(-1))) for k in got}
         res["scaling"] = "strong"
