@@ -216,10 +216,17 @@ typedef struct {
     float *peer_weights_sum[SANERF_MAX_PEERS];
     /* optional cap on the number of persistent CTAs (0 = one per SM): leaves SMs free for a concurrent kernel */
     uint32_t max_ctas;
+    /* REQUIRED device scratch of sanerf_render_workspace_bytes() bytes, 16-byte aligned: the MLP weights re-laid-out as
+     * tensor-core operand images, written by a prepare kernel at every call and staged into every CTA's shared memory by TMA */
+    void *workspace;
 } sanerf_render_args_t;
 
+#define SANERF_RENDER_WORKSPACE_BYTES 65536
+size_t sanerf_render_workspace_bytes(void);
+
 /* `model` and `args` are HOST structs (copied at launch); the pointers inside are device pointers.
- * One persistent launch renders all N rays.  Returns launch status. */
+ * One tiny prepare launch (weights -> operand images in args->workspace) + ONE persistent launch that renders all N rays.
+ * Returns launch status. */
 int sanerf_render(const sanerf_model_t *model, const sanerf_render_args_t *args, sanerf_stream_t stream);
 
 /* Standalone sample_pdf (renderer.py:84-119), perturb=False: bins [N,T0+1], weights [N,T0] ->

@@ -39,6 +39,10 @@ constexpr int kGroups = kWarps / 4;
 #ifndef SANERF_S2_XPAIR
 #define SANERF_S2_XPAIR 1   // 1: x-paired lanes in the final-stage gathers (see pair_issue); 800x800 RGB frame 11.31 -> 11.04 ms
 #endif
+#ifndef SANERF_SMEM_L0
+#define SANERF_SMEM_L0 3    // bit mask of level-0 tables pinned in shared memory (1 prop0, 2 prop1, 4 grid).  800x800 RGB frame:
+                            // none 11.07 ms, prop0 11.06, prop0+prop1 10.97, all three 11.06 (L1 shrinks from 164 to 68 KB)
+#endif
 #ifndef SANERF_PROP_DEPTH
 #define SANERF_PROP_DEPTH 1   // levels of loads in flight per chunk in the proposal gathers (1: 11.90 ms, 2: 11.99 ms)
 #endif
@@ -61,6 +65,8 @@ struct RenderParams {
     uint32_t contract, last_opaque;
     const float* u65;
     const float* u33;
+    const float* staged;   // the prepared shared-memory image (render_prepare_kernel)
+    uint32_t pin_mask;     // which of the compile-time SANERF_SMEM_L0 tables really are dense 16^3 level-0 tables
     // per call
     const float* rays_o;
     const float* rays_d;
@@ -150,7 +156,8 @@ struct LevelLoads {
     float f[3];
 };
 
-__device__ __forceinline__ void level_issue(const GridDev& g, int l, const float (&x)[3], LevelLoads& o) {
+// smem0: shared-memory copy of the level-0 table (or nullptr), used when l == 0
+__device__ __forceinline__ void level_issue(const GridDev& g, int l, const float (&x)[3], LevelLoads& o, const float2* smem0 = nullptr) {
     const uint32_t res = g.res[l];
     const uint32_t hmask = g.hmask[l];
     const float2* __restrict__ rows = reinterpret_cast<const float2*>(g.base[l]);
@@ -165,7 +172,10 @@ __device__ __forceinline__ void level_issue(const GridDev& g, int l, const float
     if (hmask == 0) {  // dense level: x + y*res + z*res^2 < rows, no modulo needed
         const uint32_t y0 = b0[1] * res, y1 = b1[1] * res, z0 = b0[2] * res * res, z1 = b1[2] * res * res;
 #pragma unroll
-        for (int i = 0; i < 8; i++) o.v[i] = __ldg(rows + (((i & 1) ? b1[0] : b0[0]) + ((i & 2) ? y1 : y0) + ((i & 4) ? z1 : z0)));
+        for (int i = 0; i < 8; i++) {
+            const uint32_t idx = ((i & 1) ? b1[0] : b0[0]) + ((i & 2) ? y1 : y0) + ((i & 4) ? z1 : z0);
+            o.v[i] = (SANERF_SMEM_L0 && smem0 && l == 0) ? smem0[idx] : __ldg(rows + idx);
+        }
     } else {
         // (x ^ y*P1 ^ z*P2) & mask == (x & mask) ^ (y*P1 & mask) ^ (z*P2 & mask): 6 ANDs + 8 three-input XORs
         const uint32_t x0 = b0[0] & hmask, x1 = b1[0] & hmask;
@@ -201,7 +211,7 @@ struct PairLoads {
     float f[3];
 };
 
-__device__ __forceinline__ void pair_issue(const GridDev& g, int l, const float (&x)[3], int xside, PairLoads& o) {
+__device__ __forceinline__ void pair_issue(const GridDev& g, int l, const float (&x)[3], int xside, PairLoads& o, const float2* smem0 = nullptr) {
     const uint32_t res = g.res[l];
     const uint32_t hmask = g.hmask[l];
     const float2* __restrict__ rows = reinterpret_cast<const float2*>(g.base[l]);
@@ -217,7 +227,10 @@ __device__ __forceinline__ void pair_issue(const GridDev& g, int l, const float 
     if (hmask == 0) {
         const uint32_t y0 = b0[1] * res, y1 = b1[1] * res, z0 = b0[2] * res * res, z1 = b1[2] * res * res;
 #pragma unroll
-        for (int i = 0; i < 4; i++) o.v[i] = __ldg(rows + (bx + ((i & 1) ? y1 : y0) + ((i & 2) ? z1 : z0)));
+        for (int i = 0; i < 4; i++) {
+            const uint32_t idx = bx + ((i & 1) ? y1 : y0) + ((i & 2) ? z1 : z0);
+            o.v[i] = (SANERF_SMEM_L0 && smem0 && l == 0) ? smem0[idx] : __ldg(rows + idx);
+        }
     } else {
         const uint32_t xm = bx & hmask;
         const uint32_t y0 = (b0[1] * 2654435761u) & hmask, y1 = (b1[1] * 2654435761u) & hmask;
@@ -245,12 +258,12 @@ __device__ __forceinline__ void pair_finish(const PairLoads& o, int xside, float
 // two points at once (two sample chunks of the same ray): twice the independent loads in flight per thread
 template <int L, int DEPTH>
 __device__ __forceinline__ void gather_levels_x2(const GridDev& g, const float (&xa)[3], const float (&xb)[3], bool ina, bool inb,
-                                                 float (&fa)[2 * L], float (&fb)[2 * L]) {
+                                                 float (&fa)[2 * L], float (&fb)[2 * L], const float2* smem0) {
     LevelLoads bufa[DEPTH], bufb[DEPTH];
 #pragma unroll
     for (int d = 0; d < DEPTH && d < L; d++) {
-        level_issue(g, d, xa, bufa[d]);
-        level_issue(g, d, xb, bufb[d]);
+        level_issue(g, d, xa, bufa[d], smem0);
+        level_issue(g, d, xb, bufb[d], smem0);
     }
 #pragma unroll
     for (int l = 0; l < L; l++) {
@@ -312,12 +325,21 @@ struct Smem {
     static constexpr int s_ds = 68;       // [128] delta*sigma / weights; [64..99] = the 33 bins of the final stage
     static constexpr int s_cdf = 196;     // [132]
     static constexpr int per_warp = 328;
-    static constexpr int total = scratch + kWarps * per_warp;
+    // optional: the dense 16^3 level-0 tables (4096 rows x 2 floats = 32 KB each) of the proposal grids / the main grid pinned
+    // in shared memory by TMA bulk copies (SANERF_SMEM_L0 bit mask: 1 prop0, 2 prop1, 4 grid); 16-byte aligned
+    static constexpr int kTabFloats = 4096 * 2;
+    static constexpr int n_tabs = ((SANERF_SMEM_L0 >> 0) & 1) + ((SANERF_SMEM_L0 >> 1) & 1) + ((SANERF_SMEM_L0 >> 2) & 1);
+    static constexpr int tabs = (scratch + kWarps * per_warp + 3) & ~3;
+    static constexpr int total = tabs + n_tabs * kTabFloats;
     static_assert(GK % 8 == 0 && GK <= 32 && HG % 16 == 0 && HG <= 64, "grid MLP widths (tc::group_layer_from_tmem)");
 };
 
+// The weights of all MLPs as the persistent CTAs want them in shared memory -- tensor-core operand images (split precision,
+// K-major core matrices), padded view-MLP rows, the two u tables -- are built ONCE per launch by this one-CTA kernel into a
+// global blob with exactly the shared-memory layout of Smem<> [0, scratch); every render CTA then stages it with a single TMA
+// bulk copy (cp.async.bulk + mbarrier expect_tx) instead of 148 CTAs each converting the nn.Linear tensors element by element.
 template <int PL, int GL, int HG, int HV>
-__device__ void stage_weights(float* sm, const RenderParams& p) {
+__global__ void __launch_bounds__(kThreads) render_prepare_kernel(const __grid_constant__ RenderParams p, float* __restrict__ sm) {
     using S = Smem<PL, GL, HG>;
     const int tid = threadIdx.x;
     for (int e = 0; e < 2; e++)
@@ -340,7 +362,6 @@ __device__ void stage_weights(float* sm, const RenderParams& p) {
         tc::stage_split_weights_bf16<HG, HG>(w1, w1 + HG * HG, p.grid_w[1], tid, kThreads);
         tc::stage_split_weights_bf16<16, HG>(w2, w2 + 16 * HG, p.grid_w[2], tid, kThreads);
     }
-    tc::fence_proxy_async_smem();  // the tensor core reads these through the async proxy
     for (int i = tid; i < 32 * S::VP; i += kThreads) {
         const int n = i / S::VP, k = i % S::VP;
         sm[S::view_w0 + i] = (n < HV && k < 31) ? __ldg(p.view_w[0] + n * 31 + k) : 0.f;
@@ -352,6 +373,7 @@ __device__ void stage_weights(float* sm, const RenderParams& p) {
     }
     for (int i = tid; i < 65; i += kThreads) sm[S::utab + i] = __ldg(p.u65 + i);
     for (int i = tid; i < 33; i += kThreads) sm[S::utab + 68 + i] = __ldg(p.u33 + i);
+    // slots the loops above do not cover (alignment gaps, table padding) stay as the caller's workspace left them: never read
 }
 
 // weights of one stage from delta*sigma (renderer.py:308-325); ds[] (shared, per warp) is
@@ -476,7 +498,7 @@ __device__ __forceinline__ bool sample_point(const RayCtx& r, float b0, float b1
 template <int PL, int GL, int HG>
 __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, int T, const float* sm, tc::Group& grp, unsigned int* free_mask,
                                                volatile int* my_slot, uint32_t tmem_base, int warp_in_group, const RayCtx& r,
-                                               const float* bins, float* ds, int lane) {
+                                               const float* bins, float* ds, int lane, const float2* smem0) {
     using S = Smem<PL, GL, HG>;
     const GridDev& g = p.prop[e];
     const float* w0 = sm + S::prop_w0 + e * 2 * 16 * S::PKP;  // hi image; lo image follows
@@ -492,7 +514,7 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, int
         float feata[S::PKP], featb[S::PKP];
         {
             float fa[2 * PL], fb[2 * PL];
-            gather_levels_x2<PL, SANERF_PROP_DEPTH>(g, xa, xb, ina, inb, fa, fb);
+            gather_levels_x2<PL, SANERF_PROP_DEPTH>(g, xa, xb, ina, inb, fa, fb, smem0);
 #pragma unroll
             for (int k = 0; k < S::PKP; k++) {
                 feata[k] = k < 2 * PL ? fa[k] : 0.f;
@@ -527,17 +549,35 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     __shared__ uint32_t tmem_base_s;
     __shared__ unsigned int tmem_free_mask;
     __shared__ int tmem_slot_of[kGroups];
+    __shared__ __align__(8) uint64_t stage_bar;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    stage_weights<PL, GL, HG, HV>(sm, p);
     if (threadIdx.x == 0) {
         for (int i = 0; i < kGroups; i++) tc::mbar_init(&mma_bar[i], 1);
+        tc::mbar_init(&stage_bar, 1);
         tc::fence_mbar_init();
         tmem_free_mask = 0xFu;
+        // TMA: the prepared weight blob (and the pinned level-0 tables) -> shared memory, completion counted in bytes on stage_bar
+        constexpr uint32_t wbytes = S::scratch * sizeof(float), tbytes = S::kTabFloats * sizeof(float);
+        tc::mbar_expect_tx(&stage_bar, wbytes + S::n_tabs * tbytes);
+        tc::tma_load_1d(tc::smem_u32(sm), p.staged, wbytes, &stage_bar);
+        int t = 0;
+        if (SANERF_SMEM_L0 & 1) tc::tma_load_1d(tc::smem_u32(sm + S::tabs + (t++) * S::kTabFloats), p.prop[0].base[0], tbytes, &stage_bar);
+        if (SANERF_SMEM_L0 & 2) tc::tma_load_1d(tc::smem_u32(sm + S::tabs + (t++) * S::kTabFloats), p.prop[1].base[0], tbytes, &stage_bar);
+        if (SANERF_SMEM_L0 & 4) tc::tma_load_1d(tc::smem_u32(sm + S::tabs + (t++) * S::kTabFloats), p.grid.base[0], tbytes, &stage_bar);
+        // (a level-0 table that is not the dense 16^3 one is copied all the same -- the first 32 KB of any table are readable --
+        // and simply not used: p.pin_mask)
     }
     if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);  // one persistent CTA per SM owns all 512 TMEM columns: 4 groups x 128
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
+    tc::mbar_wait(&stage_bar, 0);   // the bytes have landed (written and read through the async proxy: no proxy fence needed)
+    // shared-memory copies of the level-0 tables (nullptr: read through L1 like every other level); slot order = bit order
+    auto pinned = [&](int bit) -> const float2* {
+        if (!((SANERF_SMEM_L0 >> bit) & 1) || !((p.pin_mask >> bit) & 1)) return nullptr;
+        const int slot = __popc(SANERF_SMEM_L0 & ((1u << bit) - 1));
+        return reinterpret_cast<const float2*>(sm + S::tabs + slot * S::kTabFloats);
+    };
     // 4 warps = 4 rays = 128 samples of the final stage form one tensor-core group (one MMA row per thread)
     tc::Group grp = tc::make_group(tmem_base_s, kShareSlots ? 0 : (warp >> 2), warp & 3, lane, &mma_bar[warp >> 2]);
     grp.bar_id = 1 + (warp >> 2);
@@ -620,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
             const int T = st ? kMaxT / 2 : kMaxT, TN = T / 2 + 1;
             const float* bin_in = st ? b65 : nullptr;
             float* bin_out = st ? b33 : b65;
-            proposal_stage<PL, GL, HG>(p, st, T, sm, grp, &tmem_free_mask, my_slot, tmem_base, warp & 3, r, bin_in, ds, lane);
+            proposal_stage<PL, GL, HG>(p, st, T, sm, grp, &tmem_free_mask, my_slot, tmem_base, warp & 3, r, bin_in, ds, lane, pinned(st));
             weights_from_ds(ds, T, lane, last_opaque);
             __syncwarp();
             int16_t* tap = st ? p.inds1 : p.inds0;
@@ -651,8 +691,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                     for (int d = 0; d < 3; d++) px[q][d] = __shfl_sync(kFull, x01[d], 16 * q + (lane >> 1));
                 const int src = 2 * (lane & 15) + (lane >> 4);     // where this lane's own sample ends up (see below)
                 PairLoads pb[4];                                   // ring: unit u = 2 * level + pass lives in pb[u % 4]
-                pair_issue(p.grid, 0, px[0], xside, pb[0]);
-                pair_issue(p.grid, 0, px[1], xside, pb[1]);
+                pair_issue(p.grid, 0, px[0], xside, pb[0], pinned(2));
+                pair_issue(p.grid, 0, px[1], xside, pb[1], pinned(2));
                 pair_issue(p.grid, 1, px[0], xside, pb[2]);
                 pair_issue(p.grid, 1, px[1], xside, pb[3]);
 #pragma unroll 1
@@ -692,7 +732,7 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 #else
             {
                 LevelLoads buf0, buf1;             // levels 4*lb and 4*lb+1 are in flight at the top of each iteration
-                level_issue(p.grid, 0, x01, buf0);
+                level_issue(p.grid, 0, x01, buf0, pinned(2));
                 level_issue(p.grid, 1, x01, buf1);
 #pragma unroll 1
                 for (int lb = 0; lb < GKP / 8; lb++) {
@@ -948,6 +988,8 @@ template <int PL, int GL, int HG, int HV>
 static int launch_render(const RenderParams& p, bool sam, bool mask, uint32_t max_ctas, cudaStream_t st) {
     using S = Smem<PL, GL, HG>;
     const size_t smem = (size_t)S::total * sizeof(float);
+    static_assert(S::scratch * sizeof(float) <= SANERF_RENDER_WORKSPACE_BYTES, "render workspace");
+    render_prepare_kernel<PL, GL, HG, HV><<<1, kThreads, 0, st>>>(p, const_cast<float*>(p.staged));
     int dev = 0, sms = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1008,6 +1050,13 @@ int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf
     p.last_opaque = m->last_sample_opaque;
     p.u65 = m->u65;
     p.u33 = m->u33;
+    if (!a->workspace || ((uintptr_t)a->workspace & 15)) return SANERF_E_NULL;
+    p.staged = reinterpret_cast<const float*>(a->workspace);
+    {
+        // a level-0 table can be pinned in shared memory when it is the dense 16^3 one (4096 rows x 8 B = the 32 KB copied)
+        auto pinnable = [](const GridDev& g) { return g.res[0] == 16 && g.hmask[0] == 0 && g.L > 1 && g.off[1] - g.off[0] >= 4096; };
+        p.pin_mask = (pinnable(p.prop[0]) ? 1u : 0u) | (pinnable(p.prop[1]) ? 2u : 0u) | (pinnable(p.grid) ? 4u : 0u);
+    }
     p.rays_o = a->rays_o; p.rays_d = a->rays_d; p.N = a->N;
     p.cnf = a->cam_near_far; p.cnf_rows = a->cam_near_far_rows;
     p.bg = a->bg_color; p.bg_rows = a->bg_rows; p.bg_scalar = a->bg_scalar;
@@ -1035,6 +1084,8 @@ int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf
     if (PL == 4 && GL == 4 && m->grid_hidden == 16 && m->view_hidden == 16) return launch_render<4, 4, 16, 16>(p, sam, mask, a->max_ctas, st);
     return SANERF_E_CONFIG;
 }
+
+size_t sanerf_render_workspace_bytes(void) { return SANERF_RENDER_WORKSPACE_BYTES; }
 
 int sanerf_sample_pdf(const float* bins, const float* weights, const float* u, uint32_t N, uint32_t T0, uint32_t T, float* new_bins,
                       int16_t* inds, sanerf_stream_t stream) {

@@ -184,7 +184,10 @@ class FrameGather:
                     err = e
             elif err is None:
                 err = RuntimeError("a peer could not export its frame buffer")
-            self._peer = {"base": bases, "own": int(base.value or 0), "streams": [torch.cuda.Stream(device=self.device) for _ in range(self.world - 1)],
+            # SANERF_PUSH_SPLIT pieces per peer copy, each on its own stream: more copy engines in flight per push
+            self._split = max(1, int(os.environ.get("SANERF_PUSH_SPLIT", "1")))
+            self._peer = {"base": bases, "own": int(base.value or 0),
+                          "streams": [torch.cuda.Stream(device=self.device) for _ in range((self.world - 1) * self._split)],
                           "status": torch.zeros(1, dtype=torch.int32, device=self.device)}
             if err is not None:
                 raise err
@@ -229,11 +232,16 @@ class FrameGather:
         ev = torch.cuda.Event()
         ev.record()
         n = len(self._others)
-        dst = (ctypes.c_void_p * n)(*[self._peer_ptr(r, key, row0) for r in self._others])
-        streams = (ctypes.c_void_p * n)(*[s.cuda_stream for s in self._peer["streams"]])
         for s in self._peer["streams"]:
             s.wait_event(ev)
-        _lib.check(lib.sanerf_peer_push(dst, ctypes.c_void_p(self._peer_ptr(self.rank, key, row0)), nbytes, n, streams), "sanerf_peer_push")
+        piece = -(-nbytes // self._split // 256) * 256
+        for j in range(self._split):
+            off, size = j * piece, min(piece, nbytes - j * piece)
+            if size <= 0:
+                break
+            dst = (ctypes.c_void_p * n)(*[self._peer_ptr(r, key, row0) + off for r in self._others])
+            streams = (ctypes.c_void_p * n)(*[s.cuda_stream for s in self._peer["streams"][j * n:(j + 1) * n]])
+            _lib.check(lib.sanerf_peer_push(dst, ctypes.c_void_p(self._peer_ptr(self.rank, key, row0) + off), size, n, streams), "sanerf_peer_push")
         self._pushed = True
 
     def _barrier(self):
@@ -264,18 +272,24 @@ class FrameGather:
 
     def render(self, model, rays_o, rays_d, groups=1, **kw):
         """model.render / run of this rank's `n_local` rays with the results fanned out; returns the full-frame tensors.
-        `groups` > 1 renders the rows in that many equal groups so that the copy-engine push (or gather) of one group's wide
-        tensors overlaps the rendering of the next (groups must divide n_local into multiples of 128 rays)."""
+        `groups` > 1 renders the rows in that many (nearly equal) groups so that the copy-engine push of one group's wide
+        tensors overlaps the rendering of the next."""
         n = self.n_local
         assert rays_o.shape[0] == n, "FrameGather.render: every rank renders exactly n_local rays"
         feats = kw.get("return_feats", 0)
         keys = list(self.spec)
-        if groups > 1 and (n % groups or (n // groups) % 128 or self.transport == "local"):
-            groups = 1
-        step = n // groups
+        # group boundaries at multiples of 128 rays (whole tensor-core tiles), and of 4 image rows when the rays are an image
+        # block of known width (keeps the kernel's 4x4-pixel tile traversal)
+        unit = 128
+        width = kw.get("image_width")
+        if width and int(width) % 4 == 0 and n % (4 * int(width)) == 0:
+            unit = math.lcm(128, 4 * int(width))
+        n_units = n // unit if n % unit == 0 else 0
+        groups = max(1, min(int(groups), n_units)) if n_units else 1
+        bounds = [n if g == groups else (g * n_units // groups) * unit for g in range(groups + 1)] if groups > 1 else [0, n]
         kw.pop("H", None), kw.pop("W", None)
         for g in range(groups):
-            lo, hi = g * step, (g + 1) * step
+            lo, hi = bounds[g], bounds[g + 1]
             out = {k: self.slot(k, lo, hi) for k in keys}
             call = dict(kw, out=out)
             if self.transport == "peer":

@@ -403,6 +403,9 @@ class NeRFRenderer(nn.Module):
                 a.bg_scalar = float(bg_color)
         a.image, a.depth, a.weights_sum = image.data_ptr(), depth.data_ptr(), weights_sum.data_ptr()
         a.max_ctas = int(max_ctas or 0)
+        if getattr(self, "_render_ws", None) is None or self._render_ws.device != device:
+            self._render_ws = torch.empty(lib.sanerf_render_workspace_bytes(), dtype=torch.uint8, device=device)
+        a.workspace = self._render_ws.data_ptr()
         peer = None
         if peer_out:
             peer = [peer_out["image"], peer_out["depth"], peer_out["weights_sum"]]
@@ -436,7 +439,7 @@ class NeRFRenderer(nn.Module):
                 a.sam_in = sam_in.data_ptr()
             with torch.cuda.device(device), _lib.timed("render_kernel"):
                 _lib.check(lib.sanerf_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "sanerf_render")
-                _lib.count_launch()
+                _lib.count_launch(2)     # weight prepare + the persistent render kernel
             if want_sam:
                 results.update(self._feature_results(sam_in, H, W, out, feature_layout, feature_size))
             return results
@@ -452,6 +455,14 @@ class NeRFRenderer(nn.Module):
         tc_head = (width == 143 and len(net) == 3 and net[0].weight.shape == (256, 143) and net[1].weight.shape == (256, 256)
                    and net[2].weight.shape == (n_inst, 256) and n_inst <= 16 and all(l.bias is None for l in net))
         tc_head = tc_head and self.m_grid.num_levels == 16 and self.m_grid.level_dim == 8
+        if not tc_head:
+            seen = self.__dict__.setdefault("_composed_warned", set())
+            if "mask_head" not in seen and width == 143:       # default-size m_grid but a head the tensor-core kernel does not cover
+                seen.add("mask_head")
+                import warnings
+                warnings.warn("sanerf_hq_b200: the object head runs as torch nn.Linear layers (the tensor-core head covers 143 -> 256 -> "
+                              f"256 -> n_inst <= 16 without bias; this model: n_inst = {n_inst}, layers "
+                              f"{[tuple(l.weight.shape) for l in net]})", RuntimeWarning, stacklevel=3)
         # rays per launch pair (bounds the scratch: 2.3 KB per ray of records); a multiple of 4 rays = whole 128-sample tiles,
         # so the chunking is invisible in the results.  `opt.mask_chunk_rays` overrides (tests).
         cap = int(getattr(self.opt, "mask_chunk_rays", 0) or (1 << 20 if tc_head else int(getattr(self.opt, "max_ray_batch", 4096)) * 8))
@@ -491,7 +502,7 @@ class NeRFRenderer(nn.Module):
             with torch.cuda.device(device):
                 with _lib.timed("render_kernel"):
                     _lib.check(lib.sanerf_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "sanerf_render")
-                    _lib.count_launch()
+                    _lib.count_launch(2)
                 if tc_head:
                     dst = logits[head:head + n]
                     with _lib.timed("mask_head_kernel"):
