@@ -125,7 +125,7 @@ int sanerf_freq_encode_backward(const float *grad, const float *outputs, uint32_
                                 uint32_t C, float *grad_inputs, sanerf_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
- * Part 2 -- fused render (replaces NeRFRenderer.run, eval / no-grad, perturb=False)
+ * Part 2 -- fused render (replaces NeRFRenderer.run, eval / no-grad; perturb=True with caller-drawn random numbers)
  * ---------------------------------------------------------------------------------------- */
 
 #define SANERF_MAX_LEVELS 16
@@ -216,6 +216,11 @@ typedef struct {
     float *peer_weights_sum[SANERF_MAX_PEERS];
     /* optional cap on the number of persistent CTAs (0 = one per SM): leaves SMs free for a concurrent kernel */
     uint32_t max_ctas;
+    /* optional perturbed sampling (perturb=True, renderer.py:267-270 and :99-100): uniform random numbers in [0,1) drawn by the
+     * caller, noise0 [N,129] (stage-0 bin jitter), noise1 [N,65], noise2 [N,33] (sample_pdf jitter of the two resamplings) --
+     * with torch.rand in this order the stream equals the reference's rand_like calls.  All three or none.  Not available
+     * together with sam_in (SANERF_E_CONFIG). */
+    const float *noise0, *noise1, *noise2;
     /* REQUIRED device scratch of sanerf_render_workspace_bytes() bytes, 16-byte aligned: the MLP weights re-laid-out as
      * tensor-core operand images, written by a prepare kernel at every call and staged into every CTA's shared memory by TMA */
     void *workspace;

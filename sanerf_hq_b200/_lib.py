@@ -38,7 +38,7 @@ class RenderArgsT(ctypes.Structure):
                 ("mask_in_tiled", _u32), ("inds0", _vp), ("inds1", _vp), ("weights2", _vp), ("sigma2", _vp), ("bins2", _vp), ("f_image", _vp),
                 ("cam_w", _u32), ("cam_ray0", _u32), ("cam_intrinsics", _f32 * 4), ("cam_pose", _f32 * 12), ("tile_w", _u32), ("image_u8", _vp),
                 ("n_peer_out", _u32), ("peer_image", _vp * MAX_PEERS), ("peer_depth", _vp * MAX_PEERS), ("peer_weights_sum", _vp * MAX_PEERS),
-                ("max_ctas", _u32), ("workspace", _vp)]
+                ("max_ctas", _u32), ("noise0", _vp), ("noise1", _vp), ("noise2", _vp), ("workspace", _vp)]
 
 
 # name -> argtypes (restype is int for all but the two noted)

@@ -65,6 +65,7 @@ struct RenderParams {
     uint32_t contract, last_opaque;
     const float* u65;
     const float* u33;
+    const float* noise[3]; // perturb=True: uniform random numbers [N,129], [N,65], [N,33] (drawn by the caller with torch.rand)
     const float* staged;   // the prepared shared-memory image (render_prepare_kernel)
     uint32_t pin_mask;     // which of the compile-time SANERF_SMEM_L0 tables really are dense 16^3 level-0 tables
     // per call
@@ -299,7 +300,7 @@ __device__ __forceinline__ void dense(const float* __restrict__ W, const float (
 }
 
 // ---- shared memory plan ---------------------------------------------------------------------
-template <int PL, int GL, int HG>
+template <int PL, int GL, int HG, bool PERTURB = false>
 struct Smem {
     static constexpr int PK = 2 * PL, PKP = (PK + 7) & ~7;  // proposal MLP input width (padded to the MMA K step)
     static constexpr int GK = 2 * GL;                        // grid MLP input width (multiple of 4 for GL even)
@@ -324,7 +325,8 @@ struct Smem {
     static constexpr int s_b65 = 0;       // [68]  bins after the first resampling
     static constexpr int s_ds = 68;       // [128] delta*sigma / weights; [64..99] = the 33 bins of the final stage
     static constexpr int s_cdf = 196;     // [132]
-    static constexpr int per_warp = 328;
+    static constexpr int s_b129 = 328;    // [132] perturb=True only: the jittered stage-0 bins (linspace when not perturbed: never stored)
+    static constexpr int per_warp = PERTURB ? 328 + 132 : 328;
     // optional: the dense 16^3 level-0 tables (4096 rows x 2 floats = 32 KB each) of the proposal grids / the main grid pinned
     // in shared memory by TMA bulk copies (SANERF_SMEM_L0 bit mask: 1 prop0, 2 prop1, 4 grid); 16-byte aligned
     static constexpr int kTabFloats = 4096 * 2;
@@ -400,8 +402,9 @@ __device__ __forceinline__ void weights_from_ds(float* ds, int T, int lane, bool
 // writes TN new bins; cdf[] is scratch (T0+1).  u = linspace(.5/TN, 1-.5/TN, TN) table (shared).
 // T0 (<= 128) and TN are runtime values so that ONE copy of this code serves both resampling steps.
 // bins == nullptr: the input bins are linspace(0, 1, T0+1) (bin j = j / T0, exact for T0 a power of two).
+// noise != nullptr (perturb=True, renderer.py:99-100): u += (noise - 0.5) / TN with this ray's TN uniform numbers.
 __device__ __forceinline__ void sample_pdf_warp(const float* w, const float* bins, float* cdf, const float* u, float* out, int T0, int TN,
-                                                int lane, int16_t* inds_out) {
+                                                int lane, int16_t* inds_out, const float* __restrict__ noise = nullptr) {
     const float inv_t0 = 1.0f / (float)T0;
     const int per = T0 / 32;                   // <= 4
     float wp[4];
@@ -424,9 +427,11 @@ __device__ __forceinline__ void sample_pdf_warp(const float* w, const float* bin
         }
     }
     __syncwarp();
+    const float inv_tn = __frcp_rn((float)TN);   // tensor / Python scalar = multiply by the fp32 reciprocal in ATen's CUDA kernel
 #pragma unroll 1
     for (int k = lane; k < TN; k += 32) {
-        const float uk = u[k];
+        float uk = u[k];
+        if (noise) uk = __fadd_rn(uk, __fmul_rn(__fsub_rn(__ldg(noise + k), 0.5f), inv_tn));
         // searchsorted(cdf, u, right=True) = number of the T0+1 sorted entries that are <= u: branch-free descent over
         // power-of-two strides (cdf[0] = 0 <= u always; T0 + 1 <= 129 < 256)
         int lo = 0;
@@ -541,9 +546,9 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, int
     __syncwarp();
 }
 
-template <int PL, int GL, int HG, int HV, bool SAM, bool MASK>
+template <int PL, int GL, int HG, int HV, bool SAM, bool MASK, bool PERTURB>
 __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_constant__ RenderParams p) {
-    using S = Smem<PL, GL, HG>;
+    using S = Smem<PL, GL, HG, PERTURB>;
     extern __shared__ __align__(128) float sm[];
     __shared__ __align__(8) uint64_t mma_bar[kGroups];
     __shared__ uint32_t tmem_base_s;
@@ -655,16 +660,27 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
         // ---- stages 0 and 1: proposal networks + resampling.  One copy of the code serves both (runtime network index /
         // sample count): the ray loop is instruction-fetch sensitive, so its SASS footprint matters.  Stage 0 samples the
         // uniform bins linspace(0,1,129) (never stored), writes 65 bins; stage 1 reads them and writes the 33 final bins.
+        if constexpr (PERTURB) {
+            // perturb=True (renderer.py:267-270): bins = clamp(linspace(0,1,129) + (rand - 0.5) / 128, 0, 1), this ray's 129 numbers
+            float* b129 = scratch + S::s_b129;
+            const float* n0 = p.noise[0] + (size_t)ray * (kMaxT + 1);
+            for (int j = lane; j <= kMaxT; j += 32) {
+                const float b = __fadd_rn((float)j * (1.0f / kMaxT), __fmul_rn(__fsub_rn(__ldg(n0 + j), 0.5f), 1.0f / kMaxT));
+                b129[j] = fminf(fmaxf(b, 0.f), 1.f);
+            }
+            __syncwarp();
+        }
 #pragma unroll 1
         for (int st = 0; st < 2; st++) {
             const int T = st ? kMaxT / 2 : kMaxT, TN = T / 2 + 1;
-            const float* bin_in = st ? b65 : nullptr;
+            const float* bin_in = st ? b65 : (PERTURB ? scratch + S::s_b129 : nullptr);
             float* bin_out = st ? b33 : b65;
             proposal_stage<PL, GL, HG>(p, st, T, sm, grp, &tmem_free_mask, my_slot, tmem_base, warp & 3, r, bin_in, ds, lane, pinned(st));
             weights_from_ds(ds, T, lane, last_opaque);
             __syncwarp();
             int16_t* tap = st ? p.inds1 : p.inds0;
-            sample_pdf_warp(ds, bin_in, cdf, st ? u33 : u65, bin_out, T, TN, lane, (tap && active) ? tap + TN * (size_t)ray : nullptr);
+            const float* nz = PERTURB ? p.noise[1 + st] + (size_t)ray * TN : nullptr;
+            sample_pdf_warp(ds, bin_in, cdf, st ? u33 : u65, bin_out, T, TN, lane, (tap && active) ? tap + TN * (size_t)ray : nullptr, nz);
         }
 
         // ---- stage 2: the radiance field, one sample per lane -----------------------------------
@@ -984,9 +1000,9 @@ __global__ void __launch_bounds__(256) sample_pdf_kernel(const float* __restrict
 }
 
 // ---- host side -----------------------------------------------------------------------------------
-template <int PL, int GL, int HG, int HV>
+template <int PL, int GL, int HG, int HV, bool PERTURB>
 static int launch_render(const RenderParams& p, bool sam, bool mask, uint32_t max_ctas, cudaStream_t st) {
-    using S = Smem<PL, GL, HG>;
+    using S = Smem<PL, GL, HG, PERTURB>;
     const size_t smem = (size_t)S::total * sizeof(float);
     static_assert(S::scratch * sizeof(float) <= SANERF_RENDER_WORKSPACE_BYTES, "render workspace");
     render_prepare_kernel<PL, GL, HG, HV><<<1, kThreads, 0, st>>>(p, const_cast<float*>(p.staged));
@@ -998,7 +1014,7 @@ static int launch_render(const RenderParams& p, bool sam, bool mask, uint32_t ma
     const uint32_t blocks = need < (uint32_t)sms ? need : (uint32_t)sms;
 #define SANERF_LAUNCH(SAM_, MASK_)                                                                              \
     do {                                                                                                        \
-        auto kfn = render_kernel<PL, GL, HG, HV, SAM_, MASK_>;                                                  \
+        auto kfn = render_kernel<PL, GL, HG, HV, SAM_, MASK_, PERTURB>;                                         \
         if (cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) { \
             cudaGetLastError();                                                                                 \
             return SANERF_E_SMEM;                                                                               \
@@ -1006,10 +1022,16 @@ static int launch_render(const RenderParams& p, bool sam, bool mask, uint32_t ma
         cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 2048) * 100 / (228 * 1024)) + 1); \
         kfn<<<blocks, kThreads, smem, st>>>(p);                                                                 \
     } while (0)
-    if (sam && mask) SANERF_LAUNCH(true, true);
-    else if (sam) SANERF_LAUNCH(true, false);
-    else if (mask) SANERF_LAUNCH(false, true);
-    else SANERF_LAUNCH(false, false);
+    if constexpr (PERTURB) {   // perturbed sampling is instantiated for the rgb / object-head frames (trainer.py:513, 1308)
+        if (sam) return SANERF_E_CONFIG;
+        if (mask) SANERF_LAUNCH(false, true);
+        else SANERF_LAUNCH(false, false);
+    } else {
+        if (sam && mask) SANERF_LAUNCH(true, true);
+        else if (sam) SANERF_LAUNCH(true, false);
+        else if (mask) SANERF_LAUNCH(false, true);
+        else SANERF_LAUNCH(false, false);
+    }
 #undef SANERF_LAUNCH
     return check_launch();
 }
@@ -1080,8 +1102,13 @@ int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf
     const uint32_t PL = m->prop_grid[0].num_levels, GL = m->grid.num_levels;
     if (m->prop_grid[1].num_levels != PL) return SANERF_E_CONFIG;
     cudaStream_t st = (cudaStream_t)stream;
-    if (PL == 5 && GL == 16 && m->grid_hidden == 64 && m->view_hidden == 32) return launch_render<5, 16, 64, 32>(p, sam, mask, a->max_ctas, st);
-    if (PL == 4 && GL == 4 && m->grid_hidden == 16 && m->view_hidden == 16) return launch_render<4, 4, 16, 16>(p, sam, mask, a->max_ctas, st);
+    const bool perturb = a->noise0 || a->noise1 || a->noise2;
+    if (perturb && !(a->noise0 && a->noise1 && a->noise2)) return SANERF_E_NULL;
+    p.noise[0] = a->noise0; p.noise[1] = a->noise1; p.noise[2] = a->noise2;
+    if (PL == 5 && GL == 16 && m->grid_hidden == 64 && m->view_hidden == 32)
+        return perturb ? launch_render<5, 16, 64, 32, true>(p, sam, mask, a->max_ctas, st) : launch_render<5, 16, 64, 32, false>(p, sam, mask, a->max_ctas, st);
+    if (PL == 4 && GL == 4 && m->grid_hidden == 16 && m->view_hidden == 16)
+        return perturb ? launch_render<4, 4, 16, 16, true>(p, sam, mask, a->max_ctas, st) : launch_render<4, 4, 16, 16, false>(p, sam, mask, a->max_ctas, st);
     return SANERF_E_CONFIG;
 }
 

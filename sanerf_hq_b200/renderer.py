@@ -3,12 +3,12 @@
 `NeRFRenderer.render / run` keep the reference's signature, keyword arguments and result dict.
 Two execution paths produce the same numbers:
 
-* fused   -- eval / no-grad, perturb=False (every eval, test, decode and GUI call of
-             nerf/trainer.py): ONE persistent CUDA launch (`sanerf_render`, csrc/render.cu) does
+* fused   -- eval / no-grad (every eval, test, decode and GUI call of nerf/trainer.py, with or without
+             perturb): ONE persistent CUDA launch (`sanerf_render`, csrc/render.cu) does
              near/far, the three sampling stages with both proposal networks, sample_pdf,
              contraction, hash-grid lookups, the density / geometry MLP, SH, compositing and the
              deferred view MLP for all rays; `render(staged=True)` therefore does not chunk.
-* composed -- anything that needs autograd or random perturbation (training): the same algorithm
+* composed -- anything that needs autograd (training): the same algorithm
              as differentiable torch ops around this package's CUDA encoders (forward+backward).
 
 There is no CPU path: rays must be CUDA tensors.
@@ -164,7 +164,7 @@ class NeRFRenderer(nn.Module):
         if self._can_fuse(rays_o, kwargs) and not kwargs.get("return_feats", 0):
             # one persistent launch over all rays; max_ray_batch chunking only bounds the temporaries of the
             # object head
-            return self._run_fused(rays_o, rays_d, cam_near_far=cam_near_far, **kwargs)
+            return self._run_fused(rays_o, rays_d, cam_near_far=cam_near_far, noise_chunk=self.opt.max_ray_batch, **kwargs)
         N, device = rays_o.shape[0], rays_o.device
         results = {}
         out = kwargs.pop("out", None)
@@ -197,14 +197,14 @@ class NeRFRenderer(nn.Module):
         the fused kernel derives every ray from `pose` (cam2world [4,4] or [3,4]) and `intrinsics` (fx, fy, cx, cy) exactly
         like the full-image branch of the reference's nerf/utils.py::get_rays (:262-287).  Same kwargs / result dict as
         `render`; `return_uint8=True` adds `image_u8` [N,3] = (image * 255) cast like trainer.py:1140-1143.
-        Eval / perturb=False only (the fused path); the model's device is used."""
+        Eval / no-grad only (the fused path); the model's device is used."""
         device = next(self.parameters()).device
         if device.type != "cuda":
             raise RuntimeError("NeRFRenderer.render_image: the model must be on a CUDA device (there is no CPU path)")
         kw = dict(kwargs)
         kw.setdefault("perturb", False)
         if not self._can_fuse(torch.empty(0, device=device), kw):
-            raise RuntimeError("NeRFRenderer.render_image needs the fused path (eval / no-grad, perturb=False, default sample counts)")
+            raise RuntimeError("NeRFRenderer.render_image needs the fused path (eval / no-grad, default sample counts)")
         r0, r1 = (0, H) if rows is None else rows
         pose = torch.as_tensor(pose, dtype=torch.float32).reshape(-1, 4)[:3].cpu()
         camera = (pose.reshape(-1).tolist(), [float(v) for v in intrinsics], int(W), int(r0) * int(W), (int(r1) - int(r0)) * int(W), device)
@@ -235,7 +235,7 @@ class NeRFRenderer(nn.Module):
         if self._can_fuse(rays_o, kw):
             return self._run_fused(rays_o, rays_d, out=out, peer_out=peer_out, max_ctas=max_ctas, **kw)
         if peer_out:
-            raise RuntimeError("NeRFRenderer.run: peer_out needs the fused kernel (eval / no-grad, perturb=False)")
+            raise RuntimeError("NeRFRenderer.run: peer_out needs the fused kernel (eval / no-grad)")
         if not torch.is_grad_enabled() and not self.training:
             self._warn_composed(kw)
         res = self._run_composed(rays_o, rays_d, **kw)
@@ -266,8 +266,8 @@ class NeRFRenderer(nn.Module):
         """None when the configuration is one the fused kernel implements, else the reason it is not (a string)."""
         if not self.fused:
             return "model.fused is False"
-        if kw.get("perturb", False):
-            return "perturb=True draws torch random numbers per sample"
+        if kw.get("perturb", False) and self.opt.with_sam and kw.get("return_feats", 0):
+            return "perturb=True together with the SAM feature head"
         if self.opt.render_mesh:
             return "render_mesh"
         if list(self.opt.num_steps) != FUSED_NUM_STEPS:
@@ -341,7 +341,7 @@ class NeRFRenderer(nn.Module):
     @torch.no_grad()
     def _run_fused(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
                    return_feats=0, return_mask=0, H=None, W=None, taps=None, camera=None, return_uint8=False, image_width=None,
-                   out=None, peer_out=None, max_ctas=0, feature_layout=None, feature_size=None, **kwargs):
+                   out=None, peer_out=None, max_ctas=0, feature_layout=None, feature_size=None, noise_chunk=None, **kwargs):
         if camera is None:
             rays_o = rays_o.contiguous().float()
             rays_d = rays_d.contiguous().float()
@@ -420,6 +420,17 @@ class NeRFRenderer(nn.Module):
                     a.peer_weights_sum[i] = peer[2][i] + 4 * head
 
         set_peer(0)
+        if perturb:
+            # perturb=True (renderer.py:267-270, 99-100): the jitter is drawn HERE with torch.rand, in the reference's order -- per
+            # chunk of `noise_chunk` rays (what one `run` call of the reference's staged loop sees): [n,129], then [n,65], [n,33] --
+            # so that under the same torch seed the fused kernel consumes exactly the reference's random stream
+            step = int(noise_chunk or N) or 1
+            noise = [torch.empty(N, t, device=device) for t in (129, 65, 33)]
+            for head in range(0, N, step):
+                for t in noise:
+                    t[head:head + step] = torch.rand(min(step, N - head), t.shape[1], device=device)
+            a.noise0, a.noise1, a.noise2 = (t.data_ptr() for t in noise)
+            keep += noise
 
         want_sam = self.opt.with_sam and return_feats > 0
         want_mask = return_mask > 0
@@ -476,9 +487,9 @@ class NeRFRenderer(nn.Module):
             a.mask_in_tiled = 2
         sam_full = self._alloc_rows_padded(N, self.samvit_mlp[0].dim_in, device) if want_sam else None
         base = {f: getattr(a, f) for f in ("rays_o", "rays_d", "image", "depth", "weights_sum", "cam_near_far", "bg_color",
-                                           "inds0", "inds1", "weights2", "sigma2", "bins2", "f_image", "image_u8")}
+                                           "inds0", "inds1", "weights2", "sigma2", "bins2", "f_image", "image_u8", "noise0", "noise1", "noise2")}
         strides = {"rays_o": 12, "rays_d": 12, "image": 12, "depth": 4, "weights_sum": 4, "inds0": 130, "inds1": 66,
-                   "weights2": 128, "sigma2": 128, "bins2": 132, "f_image": 124, "image_u8": 3}
+                   "weights2": 128, "sigma2": 128, "bins2": 132, "f_image": 124, "image_u8": 3, "noise0": 516, "noise1": 260, "noise2": 132}
         cam_ray0 = a.cam_ray0
         user_w2 = base["weights2"]
         for head in range(0, N, chunk):
@@ -589,7 +600,7 @@ class NeRFRenderer(nn.Module):
         return out
 
     # ------------------------------------------------------------------------------------------
-    # composed path (differentiable; also the perturb=True path)
+    # composed path (differentiable: training)
     # ------------------------------------------------------------------------------------------
     def _run_composed(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
                       return_feats=0, return_mask=0, H=None, W=None, feature_layout=None, feature_size=None, **kwargs):

@@ -250,3 +250,22 @@ def test_reference_gpu_vs_cpu_oracle_floors():
         assert stats["reference_gpu@rms_floor"]["max"] <= 1e-3 and stats["candidate@rms_floor"]["max"] <= 1e-3, stats
         for k in ("image", "depth", "weights_sum"):
             assert stats["candidate/" + k]["max"] <= 1e-3, (k, stats["candidate/" + k])
+
+
+def test_perturbed_staged_render_vs_reference_gpu_same_seed():
+    """perturb=True through the staged loop (the SAM stage renders its RGB frames this way, trainer.py:513-514): the fused
+    kernel draws the jitter with torch.rand in the reference's order and chunking, so with the same torch seed both sides see
+    the same random numbers."""
+    R, cand, ref = _models("rgb")
+    ref.opt.max_ray_batch = cand.opt.max_ray_batch = 4096
+    ro, rd = _frame(4)
+    lo = 300 * W
+    ro, rd = ro[lo:lo + 20000].contiguous(), rd[lo:lo + 20000].contiguous()      # five chunks, the last one ragged
+    with torch.no_grad():
+        torch.manual_seed(21)
+        want = R.render(ref, ro, rd, staged=True, perturb=True, bg_color=1)
+        torch.manual_seed(21)
+        got = cand.render(ro, rd, staged=True, perturb=True, bg_color=1)
+        plain = cand.render(ro, rd, staged=True, perturb=False, bg_color=1)
+    assert not torch.equal(got["depth"], plain["depth"])
+    _check("perturb_rgb_staged", got, want)

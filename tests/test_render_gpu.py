@@ -251,8 +251,17 @@ def test_render_image_generates_the_rays_in_kernel(mode):
     dirs = torch.stack(((i - cx) / fx, -(j - cy) / fy, -torch.ones_like(i)), -1).reshape(-1, 3)
     want_d = dirs @ pose[:3, :3].double().t()
     assert (rays_d.double() - want_d).abs().max() < 1e-6
-    with pytest.raises(RuntimeError):
-        model.render_image(pose, intr, H, W, perturb=True)
+    # perturbed sampling through the same entry point: seeded, and different from the unperturbed frame
+    torch.manual_seed(1)
+    p1 = model.render_image(pose, intr, H, W, perturb=True, **kw)
+    torch.manual_seed(1)
+    p2 = model.render_image(pose, intr, H, W, perturb=True, **kw)
+    assert torch.equal(p1["image"], p2["image"]) and not torch.equal(p1["depth"], model.render_image(pose, intr, H, W, **kw)["depth"])
+    if mode == "rgb":
+        model.train()
+        with pytest.raises(RuntimeError):      # rgb training mode also returns losses: not a render_image case
+            model.render_image(pose, intr, H, W)
+        model.eval()
 
 
 def test_per_ray_near_far_and_background_match_oracle():
@@ -296,3 +305,33 @@ def test_full_frame_properties_and_determinism():
     assert float((a["weights_sum"] - 1).abs().max()) < 1e-5          # background == 'last_sample': the last sample is opaque
     assert float(a["depth"].min()) >= opt.min_near * 0.999
     assert float(a["image"].min()) >= 0.0 and float(a["image"].max()) <= 1.0 + 1e-5
+
+
+@pytest.mark.parametrize("mode", ["rgb", "mask"])
+def test_fused_perturb_consumes_the_reference_random_stream(mode):
+    """perturb=True (renderer.py:267-270, 99-100; trainer.py:513 renders the SAM stage's RGB frames this way, the GUI its spp
+    frames) in the fused kernel: the jitter is drawn with torch.rand in the reference's order and chunking, so under the same
+    seed the fused launch and the op-by-op path (whose agreement with the reference under a shared seed
+    tests/test_trainer_boundary_gpu.py checks) see the same random numbers and must agree like the unperturbed renders do."""
+    opt, params, specs = make_case(with_mask=mode == "mask", max_ray_batch=2048)
+    model = build_model(opt, params)
+    g = torch.Generator().manual_seed(8)
+    rays_o, rays_d = frame_rays(800, 800, pose_k=6)
+    sel = torch.randint(0, 800 * 800, (5003,), generator=g)
+    rays_o, rays_d = rays_o[sel].contiguous(), rays_d[sel].contiguous()
+    kw = dict(return_mask=1) if mode == "mask" else {}
+    for staged in (True, False):            # staged: three chunks of the random stream; non-staged: one
+        torch.manual_seed(3)
+        a = _render(model, rays_o, rays_d, staged, True, perturb=True, **kw)
+        torch.manual_seed(3)
+        b = _render(model, rays_o, rays_d, staged, False, perturb=True, **kw)
+        torch.manual_seed(3)
+        a2 = _render(model, rays_o, rays_d, staged, True, perturb=True, **kw)
+        torch.manual_seed(4)
+        c = _render(model, rays_o, rays_d, staged, True, perturb=True, **kw)
+        plain = _render(model, rays_o, rays_d, staged, True, **kw)
+        assert set(a) == set(b)
+        for k in a:
+            assert_close(a[k], b[k], REL_TOL, f"perturb/{mode}/{k}")
+            assert torch.equal(a[k], a2[k]), k
+        assert not torch.equal(a["depth"], c["depth"]) and not torch.equal(a["depth"], plain["depth"])
