@@ -236,6 +236,13 @@ class NeRFRenderer(nn.Module):
             return self._run_fused(rays_o, rays_d, out=out, peer_out=peer_out, max_ctas=max_ctas, **kw)
         if peer_out:
             raise RuntimeError("NeRFRenderer.run: peer_out needs the fused kernel (eval / no-grad)")
+        if self._can_train_heads_on_fused_geometry(rays_o, kw):
+            res = self._run_frozen_geometry(rays_o, rays_d, **kw)
+            if out:
+                for k, dst in out.items():
+                    if k in res:
+                        dst.copy_(res[k].detach().reshape(dst.shape))
+            return res
         if not torch.is_grad_enabled() and not self.training:
             self._warn_composed(kw)
         res = self._run_composed(rays_o, rays_d, **kw)
@@ -245,6 +252,46 @@ class NeRFRenderer(nn.Module):
                     dst.copy_(res[k].reshape(dst.shape))
                     res[k] = dst
         return res
+
+    def _can_train_heads_on_fused_geometry(self, rays_o, kw):
+        """Object / SAM stage training (nerf/trainer.py:401-409, 507-550) after main.py's name-based freezing (main.py:249-256): no
+        parameter of the geometry / colour field requires grad, and the heads' losses cannot reach it anyway (`weights.detach()`,
+        `geo_feat.detach()`, renderer.py:378-384).  The geometry then comes from the fused kernel (no-grad) and only the heads --
+        feature grid + MLP -- run as differentiable ops on the samples it placed."""
+        if not (torch.is_grad_enabled() and rays_o.is_cuda and not rays_o.requires_grad) or kw.get("perturb", False):
+            return False
+        feats = self.opt.with_sam and kw.get("return_feats", 0)
+        if not (kw.get("return_mask", 0) or feats) or not (self.opt.with_mask or self.opt.with_sam):
+            return False
+        if self._fuse_blocker(kw) is not None or kw.get("feature_layout") not in (None, "nhwc"):
+            return False
+        frozen = [self.grid, self.grid_mlp, self.view_mlp, self.prop_encoders, self.prop_mlp]
+        return not any(q.requires_grad for m in frozen for q in m.parameters())
+
+    def _run_frozen_geometry(self, rays_o, rays_d, bg_color=None, cam_near_far=None, return_feats=0, return_mask=0, H=None, W=None,
+                             **kwargs):
+        from .encoders import grid_encode
+        taps = {"weights2": None, "f_image": None}
+        base = self._run_fused(rays_o, rays_d, bg_color=bg_color, cam_near_far=cam_near_far, records_only=True, taps=taps)
+        N = rays_o.shape[0]
+        rec, w = base.pop("_records"), base.pop("_weights")
+        x01, geo_feat = rec[:, :3].contiguous(), rec[:, 3:].reshape(N, 32, 15)
+        results = {k: base[k] for k in ("weights_sum", "depth", "image")}
+
+        def features(enc):    # enc(xyzs, bound) on the points the kernel sampled, already mapped to [0,1]^3 (bound 0: no mapping)
+            return grid_encode(x01, enc.embeddings, enc.offsets, enc.per_level_scale, enc.base_resolution, False, enc.gridtype_id,
+                               enc.align_corners, enc.interp_id, None, 0.0).view(N, 32, -1)
+
+        if self.opt.with_sam:
+            f_sam = torch.sum(w.unsqueeze(-1) * features(self.s_grid), dim=-2)                                  # renderer.py:361
+            f = torch.cat([f_sam, taps["f_image"], results["image"], results["depth"].unsqueeze(-1)], dim=-1)  # :363
+            samvit = self.samvit_mlp(f)
+            if return_feats > 0:
+                results["samvit"] = samvit.view(H, W, -1)
+        if return_mask > 0:
+            point_masks = self.mask_mlp(torch.cat([features(self.m_grid), geo_feat], dim=-1))                   # :378-381
+            results["instance_mask_logits"] = torch.sum(w.unsqueeze(-1) * point_masks, dim=-2)                 # :384
+        return results
 
     def _warn_composed(self, kw):
         """Eval-mode call that cannot take the single-launch kernel: say so once per reason instead of silently running ~10x
@@ -341,7 +388,8 @@ class NeRFRenderer(nn.Module):
     @torch.no_grad()
     def _run_fused(self, rays_o, rays_d, bg_color=None, perturb=False, cam_near_far=None, update_proposal=True,
                    return_feats=0, return_mask=0, H=None, W=None, taps=None, camera=None, return_uint8=False, image_width=None,
-                   out=None, peer_out=None, max_ctas=0, feature_layout=None, feature_size=None, noise_chunk=None, **kwargs):
+                   out=None, peer_out=None, max_ctas=0, feature_layout=None, feature_size=None, noise_chunk=None, records_only=False,
+                   **kwargs):
         if camera is None:
             rays_o = rays_o.contiguous().float()
             rays_d = rays_d.contiguous().float()
@@ -434,6 +482,8 @@ class NeRFRenderer(nn.Module):
 
         want_sam = self.opt.with_sam and return_feats > 0
         want_mask = return_mask > 0
+        if records_only:      # geometry only: per-sample records (point, geo_feat) + weights for differentiable heads on top
+            want_sam, want_mask = False, True
         if taps is not None:  # parity taps (tests): dict name -> None, filled with tensors
             shapes = {"inds0": ((N, 65), torch.int16), "inds1": ((N, 33), torch.int16), "weights2": ((N, 32), torch.float32),
                       "sigma2": ((N, 32), torch.float32), "bins2": ((N, 33), torch.float32), "f_image": ((N, 31), torch.float32)}
@@ -459,6 +509,22 @@ class NeRFRenderer(nn.Module):
         # tensor-core head (csrc/heads.cu) gathers m_grid, runs mask_mlp 143 -> 256 -> 256 -> n_inst and composites, one launch
         # per chunk of rays (the chunk bounds the scratch).  Other widths (config #1's small network, n_inst > 16): the fused
         # kernel writes the full per-sample inputs cat[m_grid(x), geo_feat] and the nn.Module MLP consumes them.
+        if records_only:
+            n_pad = -(-max(N, 1) // 4) * 4
+            mask_in = torch.empty(n_pad * 32 * 18, device=device)
+            w2 = torch.empty(n_pad, 32, device=device)
+            a.mask_in, a.mask_in_tiled = mask_in.data_ptr(), 2
+            if not a.weights2:
+                a.weights2 = w2.data_ptr()
+            else:
+                w2 = taps["weights2"]
+            with torch.cuda.device(device), _lib.timed("render_kernel"):
+                _lib.check(lib.sanerf_render(ctypes.byref(model), ctypes.byref(a), _lib.stream_ptr()), "sanerf_render")
+                _lib.count_launch(2)
+            # records are tile-transposed [tile][18][128] (row = ray * 32 + sample): back to [N * 32, 18]
+            results["_records"] = mask_in.view(-1, 18, 128).permute(0, 2, 1).reshape(-1, 18)[:N * 32]
+            results["_weights"] = w2[:N]
+            return results
         n_inst = self.opt.n_inst
         logits = result("instance_mask_logits", N, n_inst)
         width = self.mask_mlp[0].dim_in

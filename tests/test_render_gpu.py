@@ -335,3 +335,52 @@ def test_fused_perturb_consumes_the_reference_random_stream(mode):
             assert_close(a[k], b[k], REL_TOL, f"perturb/{mode}/{k}")
             assert torch.equal(a[k], a2[k]), k
         assert not torch.equal(a["depth"], c["depth"]) and not torch.equal(a["depth"], plain["depth"])
+
+
+@pytest.mark.parametrize("mode", ["sam", "mask"])
+def test_head_training_on_frozen_geometry_runs_the_fused_kernel(mode):
+    """Object / SAM stage training after main.py's name-based freezing (main.py:249-256; trainer.py:401-409, 507-550): the
+    geometry comes from the fused kernel (no-grad), only the head's feature grid + MLP run as differentiable ops on the samples
+    it placed.  Outputs and gradients must match the op-by-op path."""
+    from sanerf_hq_b200 import _lib
+    opt, params, specs = make_case(with_sam=mode == "sam", with_mask=mode == "mask")
+    model = build_model(opt, params).train()
+    heads = ("s_grid", "samvit_mlp") if mode == "sam" else ("m_grid", "mask_mlp")
+    for n, q in model.named_parameters():
+        q.requires_grad = n.startswith(heads)
+    g = torch.Generator().manual_seed(12)
+    rays_o, rays_d = frame_rays(800, 800, pose_k=10)
+    sel = torch.randint(0, 800 * 800, (1024,), generator=g)
+    rays_o, rays_d = rays_o[sel].contiguous().to(DEV), rays_d[sel].contiguous().to(DEV)
+    kw = dict(return_feats=1, H=32, W=32) if mode == "sam" else dict(return_mask=1)
+    key = "samvit" if mode == "sam" else "instance_mask_logits"
+    target = torch.randn(1024, 256 if mode == "sam" else 2, generator=g).to(DEV)
+
+    def step(fused):
+        model.fused = fused
+        model.zero_grad(set_to_none=True)
+        n0 = _lib.launch_counter["n"]
+        out = model.render(rays_o, rays_d, staged=False, perturb=False, update_proposal=False, **kw)
+        used_fused_kernel = "render" if fused else None
+        loss = (out[key].reshape(target.shape) - target).pow(2).mean()
+        loss.backward()
+        grads = {n: q.grad.detach().clone() for n, q in model.named_parameters() if q.grad is not None}
+        return out, float(loss), grads, _lib.launch_counter["n"] - n0, used_fused_kernel
+
+    a, la, ga, launches, _ = step(True)
+    b, lb, gb, _, _ = step(False)
+    model.fused = True
+    assert launches >= 2 and all(n.startswith(heads) for n in ga) and set(ga) == set(gb)
+    assert set(a) == set(b)
+    for k in a:
+        assert_close(a[k], b[k], REL_TOL, f"frozen/{mode}/{k}")
+    assert abs(la - lb) <= 1e-4 * abs(lb)
+    # gradients: the two paths place the samples / evaluate geo_feat with different (split-precision vs cuBLAS) arithmetic, and
+    # leaky_relu's derivative is discontinuous where a pre-activation is ~0, so single entries may move by a percent of the scale
+    for n in ga:
+        scale = float(gb[n].abs().max())
+        assert scale > 0 and float((ga[n] - gb[n]).abs().max()) <= 2e-2 * scale, n
+        assert float((ga[n] - gb[n]).norm()) <= 1e-2 * float(gb[n].norm()), n
+    # with a trainable geometry parameter the call must fall back to the fully differentiable path
+    model.grid_mlp.net[0].weight.requires_grad = True
+    assert not model._can_train_heads_on_fused_geometry(rays_o, dict(kw, perturb=False))
