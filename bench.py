@@ -266,21 +266,28 @@ def ref_gpu_baseline(wl, model, dev, H, W, poses, intr, cand_out0):
                 key = "rows_5_per_call_4000_rays"
             out[key] = {"value": n / (ms * 1e-3) / 1e6, "ms_per_frame": ms}
         # parity of the candidate's pose-0 frame against the reference's (same rays)
-        dev_max = {}
+        dev_max, dev_frac = {}, {}
         for k, rv in first.items():
             if torch.is_tensor(rv) and k in cand_out0:
                 cv = cand_out0[k].reshape(rv.shape)
                 floor = 1e-3
                 if k in ("samvit", "instance_mask_logits"):
                     floor = max(1e-3, 0.1 * float(rv.double().pow(2).mean().sqrt()))
-                worst = 0.0
+                worst, beyond = 0.0, 0
                 cf, rf = cv.reshape(-1), rv.reshape(-1)
                 for head in range(0, rf.numel(), 1 << 24):
                     x, y = cf[head:head + (1 << 24)].double(), rf[head:head + (1 << 24)].double()
-                    worst = max(worst, float(((x - y).abs() / y.abs().clamp(min=floor)).max()))
+                    e = (x - y).abs() / y.abs().clamp(min=floor)
+                    worst = max(worst, float(e.max()))
+                    beyond += int((e > 1e-3).sum())
                 dev_max[k] = worst
+                dev_frac[k] = beyond / max(1, rf.numel())
         out["candidate_max_rel_dev_pose0"] = dev_max
-        out["tolerance"] = "|cand - ref| <= 1e-3 * max(|ref|, floor); floor 1e-3 (samvit / logits: max(1e-3, 0.1 rms))"
+        out["candidate_frac_beyond_tolerance_pose0"] = dev_frac
+        out["tolerance"] = ("|cand - ref| <= 1e-3 * max(|ref|, floor); floor 1e-3 (samvit / logits: max(1e-3, 0.1 rms)).  A few rays per frame "
+                            "(near-ties in sample_pdf, amplified by the head MLPs) exceed it between ANY two fp32 evaluations of the reference "
+                            "algorithm -- the reference GPU against itself at another batch shape, or against the CPU oracle: "
+                            "tests/test_ref_gpu_frames.py arbitrates those rays")
     del ref
     torch.cuda.empty_cache()
     return out

@@ -17,7 +17,8 @@ feature vectors (samvit, instance_mask_logits) floor = max(1e-3, 0.1 * rms(ref))
 oracle at both floors (measured on B200: the reference's GPU samvit is 1.7e-2 away from the CPU oracle at the strict floor, i.e.
 the strict floor is not a property of the algorithm in fp32; 2.9e-4 at the rms floor).
 
-Arbitration for the 256-d SAM feature: the 5-layer MLP + LayerNorm amplifies a one-ulp difference in a resampled bin, so
+Arbitration for the signed feature vectors: the head MLPs amplify a one-ulp difference in a resampled bin (a near-tie in
+sample_pdf moves a sample), so
 on a whole frame (164 M values) two fp32 evaluations of the reference algorithm disagree beyond 1e-3 on a handful of rays --
 measured: on the worst ray of pose 11 the reference's GPU path is 2.6e-2 away from the CPU oracle while the candidate is 2e-4 away
 from it; on another ray the reference GPU's own frame and its run on that ray alone differ by 1.3e-3, the candidate agrees with
@@ -177,7 +178,7 @@ def test_mask_full_frame_and_train_batch_vs_reference_gpu():
         want = R.render(ref, ro, rd, staged=True, perturb=False, bg_color=1, return_mask=1)
         got = cand.render(ro, rd, staged=True, perturb=False, bg_color=1, return_mask=1)
     assert "instance_mask_logits" in want and want["instance_mask_logits"].shape == (H * W, 2)
-    _check("config4_mask_frame", got, want, signed=("instance_mask_logits",))
+    _check("config4_mask_frame", got, want, signed=("instance_mask_logits",), arb=("mask", cand, ro, rd, dict(return_mask=1), R, ref))
     del want, got
     # (ii) 6000 uniformly random pixels across 24 seeded poses, then 4 local 8x8 patches (global rays first)
     g = torch.Generator().manual_seed(17)
@@ -200,7 +201,7 @@ def test_mask_full_frame_and_train_batch_vs_reference_gpu():
         # the trainer's call shape (trainer.py:407-409): non-staged, update_proposal=False, return_mask=1
         want = R.render(ref, ro, rd, staged=False, perturb=False, bg_color=1, update_proposal=False, return_mask=1)
         got = cand.render(ro, rd, staged=False, perturb=False, bg_color=1, update_proposal=False, return_mask=1)
-    _check("config4_mask_train_batch", got, want, signed=("instance_mask_logits",))
+    _check("config4_mask_train_batch", got, want, signed=("instance_mask_logits",), arb=("mask", cand, ro, rd, dict(return_mask=1), R, ref))
     s = STATS["config4_mask_frame"]["instance_mask_logits@rms_floor"], STATS["config4_mask_train_batch"]["instance_mask_logits@rms_floor"]
     assert max(x["max"] for x in s) <= 1e-3, s
 
