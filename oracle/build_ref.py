@@ -10,8 +10,10 @@ with a flag-only change: -std=c++17 instead of the reference's -std=c++14
 keeps its -use_fast_math (freqencoder/backend.py:9).
 
 The modules need a GPU to *run*; they are used on the GPU box by
-tests/test_ref_cuda_gpu.py (new kernels vs the reference's kernels) and by
-bench.py's optional "ref_gpu" figure.  oracle/_ref/ is git-ignored but ships
+tests/test_ref_cuda_gpu.py / test_ref_cuda_bwd_gpu.py (new kernels vs the
+reference's kernels), and -- together with the reference's byte-compiled Python
+(oracle/stage_ref.py) through oracle/ref_runtime.py -- by the full-frame parity
+tests, the reference-Trainer tests and bench.py's `ref_gpu_baseline`.  oracle/_ref/ is git-ignored but ships
 with gpurun.  Takes ~15 min on 8 cores; run once:
 
     python oracle/build_ref.py            # all three
