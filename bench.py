@@ -410,12 +410,15 @@ def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, ste
         host_out = {k: torch.empty((n_total,) + s).pin_memory() for k, s in spec.items()} if rank == 0 else None
         o_dev, d_dev = torch.empty(n_local, 3, device=dev), torch.empty(n_local, 3, device=dev)
 
+        skip = os.environ.get("SANERF_E2E_SKIP", "")      # debugging aid: "h2d" / "d2h" leave that copy out
+
         def step_e2e(i):
             ho, hd = host_rays[i % n_res]
-            o_dev.copy_(ho, non_blocking=True)
-            d_dev.copy_(hd, non_blocking=True)
+            if "h2d" not in skip:
+                o_dev.copy_(ho, non_blocking=True)
+                d_dev.copy_(hd, non_blocking=True)
             out = render_frame(o_dev, d_dev)
-            if host_out is not None:
+            if host_out is not None and "d2h" not in skip:
                 for k in keys:
                     host_out[k].copy_(out[k], non_blocking=True)
 

@@ -5,12 +5,13 @@ No collective touches the data path before compositing: rays are independent (ev
 axis).  The only exchange is that of the per-ray results, the role of the reference's (dead) eval-time
 `dist.all_gather(preds)` (nerf/trainer.py:1582-1601).  Two transports behind `FrameGather`:
 
-* "peer"  (CUDA, one node) -- every rank owns full-frame buffers in NVLink peer memory (csrc/peer.cu, CUDA IPC).  The fused
-          render kernel stores image / depth / weights_sum of its rays straight into every peer's buffer next to its own
-          (`sanerf_render_args_t::peer_*`): the kernel's final stores ARE the all-gather.  Wide tensors (the 256-d SAM feature,
-          1 KB per ray) and the object logits are pushed by the copy engines row group by row group while the SMs already
-          render the next group; a frame ends with one flag barrier.  No collective kernel, no pack / unpack copies, no SM
-          spent on communication.
+* "peer"  (CUDA, one node) -- every rank owns full-frame buffers in NVLink peer memory (csrc/peer.cu, CUDA IPC).  A rank's
+          rows reach the peers by copy-engine pushes (cudaMemcpyAsync peer copies on side streams), row group by row group
+          while the SMs already render the next group -- what makes the 256-d SAM feature (1 KB per ray) affordable; a frame
+          ends with one flag barrier.  No collective kernel, no pack / unpack copies, no SM spent on communication.
+          Optionally (`kernel_stores=True`) the fused render kernel stores image / depth / weights_sum of its rays straight
+          into every peer's buffer next to its own (`sanerf_render_args_t::peer_*`), i.e. the kernel's final stores are the
+          all-gather of the narrow outputs; measured slightly slower than the pushes (see __init__), so off by default.
 * "nccl"  (any backend, also gloo on CPU) -- the kernels store into the rank's slot of the full-frame tensors and one in-place
           `all_gather_into_tensor` per key gathers them (no pack / unpack copies either).
 
@@ -116,7 +117,7 @@ class FrameGather:
     rows because sharding does not change per-ray arithmetic.  Buffers are double-buffered: the tensors returned for frame i
     stay valid until frame i+2 is rendered, provided their consumers were enqueued on the current stream."""
 
-    def __init__(self, n_local, spec, device, group=None, transport="auto", n_buffers=2, timeout_s=20.0):
+    def __init__(self, n_local, spec, device, group=None, transport="auto", n_buffers=2, timeout_s=20.0, kernel_stores=None):
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -126,6 +127,11 @@ class FrameGather:
             transport = os.environ.get("SANERF_TRANSPORT", "peer" if (self.device.type == "cuda" and 1 < self.world <= 8) else "nccl")
         self.transport = transport if self.world > 1 else "local"
         self._peer = None
+        # kernel_stores (or SANERF_PEER_KERNEL_STORES=1): the render kernel stores image / depth / weights_sum straight into the
+        # peers' buffers; default off = the copy engines push them like the wide keys.  Measured at 8 GPUs (rgb, ms per step):
+        # in-kernel stores 11.67-11.72, copy-engine pushes 11.49; at 2 GPUs the in-kernel stores showed erratic steps in one
+        # of three runs (remote stores hold LSU slots while the peer's own gathers saturate its L2), the pushes did not.
+        self._kernel_stores = (os.environ.get("SANERF_PEER_KERNEL_STORES", "0") == "1") if kernel_stores is None else bool(kernel_stores)
         n_total = self.n_local * self.world
         if self.transport == "peer":
             try:
@@ -292,7 +298,7 @@ class FrameGather:
             lo, hi = bounds[g], bounds[g + 1]
             out = {k: self.slot(k, lo, hi) for k in keys}
             call = dict(kw, out=out)
-            if self.transport == "peer":
+            if self.transport == "peer" and self._kernel_stores:
                 call["peer_out"] = {k: [self._peer_ptr(r, k, self.rank * n + lo) for r in self._others] for k in NARROW_KEYS if k in self.spec}
             if feats:
                 # the reference's `samvit.view(H, W, -1)` (renderer.py:371-372) only needs H*W == rays of the call
@@ -302,7 +308,7 @@ class FrameGather:
                 model.render(rays_o[lo:hi], rays_d[lo:hi], staged=True, **call)
             if self.transport == "peer":
                 for k in keys:
-                    if k not in NARROW_KEYS:
+                    if k not in NARROW_KEYS or not self._kernel_stores:
                         self._push(k, lo, hi)
         full = self.buffers[self.frame % len(self.buffers)]
         if self.transport == "peer":

@@ -40,8 +40,8 @@ def main():
             if wl == "mask":
                 spec["instance_mask_logits"] = (2,)
                 kw = dict(return_mask=1)
-            for transport in ("peer", "nccl"):
-                fg = FrameGather(rows * W, spec, dev, transport=transport)
+            for transport, kstores in (("peer", False), ("peer", True), ("nccl", False)):   # CE pushes | in-kernel peer stores | NCCL
+                fg = FrameGather(rows * W, spec, dev, transport=transport, kernel_stores=kstores)
                 for frame, groups in enumerate((1, 4, 2)):
                     intr = lego_intrinsics(H, W)
                     ro, rd = get_rays(orbit_pose(3 + frame).to(dev), intr, H, W, device=dev)
@@ -54,7 +54,7 @@ def main():
                         want = model.render(ro, rd, staged=True, perturb=False, **kw)
                     fg.check()
                     same = {k: bool(torch.equal(got[k], want[k].reshape(got[k].shape))) for k in spec}
-                    report["cases"][f"{wl}/{fg.transport}(asked {transport})/frame{frame}/groups{groups}"] = same
+                    report["cases"][f"{wl}/{fg.transport}(asked {transport}, kernel_stores={kstores})/frame{frame}/groups{groups}"] = same
                     report["ok"] &= all(same.values())
                 fg.close()
             del model
