@@ -352,6 +352,20 @@ class NeRFRenderer(nn.Module):
             dst.res[i] = r
 
     def _model_struct(self, device):
+        """sanerf_model_t for the current parameters.  Filling the ctypes struct costs ~200 field stores; it is rebuilt only when
+        a tensor it points to moved (load_state_dict / .to() / optimizer steps keep data_ptr), the mode or the box changed."""
+        tensors = [self.grid.embeddings, self.prop_encoders[0].embeddings, self.prop_encoders[1].embeddings]
+        tensors += [l.weight for net in (self.grid_mlp, self.view_mlp, self.prop_mlp[0], self.prop_mlp[1]) for l in net.net]
+        if self.opt.with_sam:
+            tensors.append(self.s_grid.embeddings)
+        if self.opt.with_mask and self.opt.mask_mlp_type == "default":
+            tensors.append(self.m_grid.embeddings)
+        box = self.aabb_train if self.training else self.aabb_infer
+        ckey = (tuple(t.data_ptr() for t in tensors), box.data_ptr(), box._version, str(device), self.min_near, float(self.bound),
+                bool(self.opt.contract), self.opt.background, getattr(self.opt, "n_inst", 0), self._aabb_host[0])
+        cached = self.__dict__.get("_model_cache")
+        if cached is not None and cached[0] == ckey:
+            return cached[1], list(cached[2])
         m = _lib.ModelT()
         keep = []
         for i in range(2):
@@ -369,7 +383,6 @@ class NeRFRenderer(nn.Module):
         if self.opt.with_mask and self.opt.mask_mlp_type == "default":
             self._fill_grid(m.m_grid, self.m_grid)
             m.n_inst = self.opt.n_inst
-        box = self.aabb_train if self.training else self.aabb_infer
         key = (box.data_ptr(), box._version)
         if self._aabb_host[0] != key:  # host copy cached so a render call does not sync the stream
             self._aabb_host = (key, box.tolist())
@@ -383,6 +396,7 @@ class NeRFRenderer(nn.Module):
         u65, u33 = self._u_table(65, device), self._u_table(33, device)
         m.u65, m.u33 = u65.data_ptr(), u33.data_ptr()
         keep += [u65, u33]
+        self.__dict__["_model_cache"] = ((ckey[:-1] + (self._aabb_host[0],)), m, list(keep))
         return m, keep
 
     @torch.no_grad()

@@ -122,3 +122,32 @@ def test_torch_helpers_match_reference_fixture():
             out = mod.sample_pdf(t(f"pdf{T0}_bins"), t(f"pdf{T0}_weights"), T)
             out = out[0] if isinstance(out, tuple) else out
             assert same(out, t(f"pdf{T0}_out")), (mod.__name__, T0)
+
+
+def test_oracle_matches_the_reference_python_run_live():
+    """Besides the committed fixtures: when the reference's own Python is staged (oracle/_ref/bytecode, built by
+    oracle/stage_ref.py where /root/reference is mounted) it is imported here and run on CPU -- its `_gridencoder` /
+    `_shencoder` imports served by the C restatement -- and the oracle's restatement of `run()` must reproduce it exactly,
+    for all three workloads, staged and non-staged."""
+    import warnings
+    from oracle import ref_runtime as R
+    if not R.available("cpu"):
+        pytest.skip("oracle/_ref/bytecode is not staged (python oracle/stage_ref.py)")
+    for with_sam, with_mask in ((False, False), (True, False), (False, True)):
+        opt = O.default_opt(with_sam=with_sam, with_mask=with_mask, max_ray_batch=64)
+        specs = O.default_specs(2)
+        params, specs = O.make_params(opt, specs, seed=11)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            model = R.build_network(opt, params, device="cpu", backend="cpu")
+        rays_o, rays_d = O.get_rays(O.orbit_pose(9), 800, 800)
+        sel = torch.arange(0, 150) * 4001 % (800 * 800)
+        rays_o, rays_d = rays_o[sel].contiguous(), rays_d[sel].contiguous()
+        kw = dict(return_feats=1, H=10, W=15) if with_sam else (dict(return_mask=1) if with_mask else {})
+        with torch.no_grad(), warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = R.render(model, rays_o, rays_d, backend="cpu", staged=not with_sam, perturb=False, bg_color=1, **kw)
+        got = O.render(params, specs, opt, rays_o, rays_d, staged=not with_sam, bg_color=1, **kw)
+        for k, v in want.items():
+            if torch.is_tensor(v):
+                assert torch.equal(got[k].reshape(v.shape), v), (with_sam, with_mask, k)
