@@ -344,9 +344,11 @@ def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, ste
 
     flush = None if args.no_l2_flush else ctx["flush"]
 
-    def timed_loop(step_fn, n_steps, n_warm):
+    def timed_loop(step_fn, n_steps, n_warm, finish_fn=None):
         for i in range(n_warm):
             step_fn(i)
+        if finish_fn is not None:
+            finish_fn()
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -359,6 +361,8 @@ def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, ste
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record()
             step_fn(n_warm + i)
+            if finish_fn is not None and i == n_steps - 1:
+                finish_fn()                    # drain what the last step left in flight: inside the timed region
             b.record()
             evs.append((a, b))
         torch.cuda.synchronize()
@@ -425,6 +429,51 @@ def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, ste
         e2e_ms = timed_loop(step_e2e, steps, warmup)[0] / steps
         e2e_value = n_total / (e2e_ms * 1e-3) / 1e6
 
+        # ---- the same, streamed: the H2D of frame i+1 and the D2H of frame i-1 run on a copy stream while frame i renders
+        # (double-buffered ray buffers; FrameGather double-buffers the results).  Every copy is waited for by the main stream
+        # inside a timed step, the last D2H inside the last one.
+        copy_stream = torch.cuda.Stream(device=dev)
+        ray_buf = [(torch.empty(n_local, 3, device=dev), torch.empty(n_local, 3, device=dev)) for _ in range(2)]
+        h2d_done, rays_free, d2h_done = [None, None], [None, None], [None]
+
+        def prefetch(i):
+            slot = i % 2
+            ho, hd = host_rays[i % n_res]
+            with torch.cuda.stream(copy_stream):
+                if rays_free[slot] is not None:
+                    copy_stream.wait_event(rays_free[slot])
+                ray_buf[slot][0].copy_(ho, non_blocking=True)
+                ray_buf[slot][1].copy_(hd, non_blocking=True)
+                h2d_done[slot] = torch.cuda.Event()
+                h2d_done[slot].record(copy_stream)
+
+        def step_stream(i):
+            slot, main = i % 2, torch.cuda.current_stream(dev)
+            if h2d_done[slot] is None:
+                prefetch(i)
+            main.wait_event(h2d_done[slot])
+            h2d_done[slot] = None
+            prefetch(i + 1)
+            out = render_frame(*ray_buf[slot])
+            rays_free[slot] = torch.cuda.Event()
+            rays_free[slot].record(main)
+            if d2h_done[0] is not None:
+                main.wait_event(d2h_done[0])          # the previous frame has left the device before this step ends
+            if host_out is not None:
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(rays_free[slot])
+                    for k in keys:
+                        host_out[k].copy_(out[k], non_blocking=True)
+                    d2h_done[0] = torch.cuda.Event()
+                    d2h_done[0].record(copy_stream)
+
+        def drain():
+            if d2h_done[0] is not None:
+                torch.cuda.current_stream(dev).wait_event(d2h_done[0])
+
+        stream_ms = timed_loop(step_stream, steps, warmup, finish_fn=drain)[0] / steps
+        stream_value = n_total / (stream_ms * 1e-3) / 1e6
+
         # ---- informational: the same frame through render_image: host pose in (64 B), 8-bit image out -------
         cam_value = None
         if wl == "rgb" and world == 1 and headline:
@@ -486,7 +535,9 @@ def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, ste
             "kernels": kernels,
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * n_local * 12 * world,
                     "d2h_bytes_per_step": int(sum(t.numel() * 4 for t in host_out.values())),
-                    "d2h": "rank 0 reads every gathered output: " + ", ".join(keys), "render_image_uint8_value": cam_value},
+                    "d2h": "rank 0 reads every gathered output: " + ", ".join(keys), "render_image_uint8_value": cam_value,
+                    "streamed_value": stream_value, "streamed_ms_per_step": stream_ms,
+                    "streamed": "same copies, on a copy stream: H2D of the next and D2H of the previous frame overlap the render"},
             "gpu_launches": int(launches),
             "checksum_pose0": {k: float(v.double().sum()) for k, v in out0.items()},
         }
