@@ -128,6 +128,10 @@ __device__ __forceinline__ void issue_ksteps(uint32_t d_tmem, uint32_t a_col, ui
 // Measured and rejected: x-paired producer gathers (8 lanes per sample, the x-neighbours of a corner fetched by adjacent lanes:
 // 1/3 fewer L1 line lookups, 40 % more producer instructions): 13.1 -> 15.7 ms per frame -- the producers are issue-bound as
 // much as L1-bound.  (The same pairing pays in the render kernel's final stage, whose C=2 gathers are L1-bound: render.cu.)
+// Also without effect (round 2): sharing the cell lookups among the four lanes of a sample (one lookup + 9 SHFL per level instead
+// of four lookups, -25 % producer instructions): 13.45 -> 13.42 ms; the same with four levels = 32 loads in flight per lane: 13.28.
+// Neither fewer producer instructions nor more loads in flight move the kernel: per tile the tensor pipe is busy 5.2 of 12.2 us
+// and the rest is the serial MMA <-> epilogue chain of ONE tile -- tensor memory (2 x 256 columns) holds a single tile in flight.
 #ifndef SANERF_MASK_PRODUCER_WARPS
 #define SANERF_MASK_PRODUCER_WARPS 16
 #endif
