@@ -33,7 +33,7 @@ import os
 import pytest
 import torch
 
-from helpers import REPO, O
+from helpers import REPO
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
