@@ -3,6 +3,10 @@
 #pragma once
 #include "common.cuh"
 
+#ifndef SANERF_FFMA2
+#define SANERF_FFMA2 1
+#endif
+
 namespace sanerf {
 
 constexpr unsigned kFullMask = 0xffffffffu;
@@ -26,6 +30,30 @@ __device__ __forceinline__ void floor_split(float pos, uint32_t& cell, float& fr
     cell = __float_as_uint(t) & 0x007fffffu;
     frac = pos - (t - 8388608.0f);
 }
+
+// Packed FP32 FMA of sm_100a (fma.rn.f32x2 -> SASS FFMA2 with a scalar-broadcast operand): acc.{x,y} = fma(w, v.{x,y}, acc.{x,y}),
+// bit-identical to the two scalar FMAs it replaces (IEEE fma per component).  The FMA pipe needs two cycles for it
+// (tools/ffma2_rate.cu: 2.07 vs 2.16 cycles per pair), but it takes ONE issue slot instead of two -- the trilinear blends are where
+// the render kernels spend a sixth of their issue slots.
+struct Acc2 {
+    unsigned long long bits;
+    __device__ __forceinline__ Acc2() : bits(0ull) {}     // {0.f, 0.f}
+    __device__ __forceinline__ void fma(float w, float2 v) {
+#if SANERF_FFMA2
+        unsigned long long wv, vv;
+        asm("mov.b64 %0, {%1,%1};" : "=l"(wv) : "f"(w));
+        asm("mov.b64 %0, {%1,%2};" : "=l"(vv) : "f"(v.x), "f"(v.y));
+        asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(bits) : "l"(wv), "l"(vv));
+#else
+        float a0, a1;
+        get(a0, a1);
+        a0 = __fmaf_rn(w, v.x, a0);
+        a1 = __fmaf_rn(w, v.y, a1);
+        asm("mov.b64 %0, {%1,%2};" : "=l"(bits) : "f"(a0), "f"(a1));
+#endif
+    }
+    __device__ __forceinline__ void get(float& a0, float& a1) const { asm("mov.b64 {%0,%1}, %2;" : "=f"(a0), "=f"(a1) : "l"(bits)); }
+};
 
 // ---- C=8 feature grids: quarter-row gathers -------------------------------------------------------------------------
 // A C=8 row is 32 bytes.  "lane = sample, two LDG.128 per corner" costs 2 L1 tag cycles per distinct 128-byte line per
@@ -57,17 +85,15 @@ __device__ __forceinline__ void quarter_level(const GridDev& g, int l, const flo
 #pragma unroll
         for (int i = 0; i < 8; i++) v[i] = __ldg(rows + 4 * (((i & 1) ? x1 : x0) ^ ((i & 2) ? y1 : y0) ^ ((i & 4) ? z1 : z0)));
     }
-    float a0 = 0.f, a1 = 0.f;
+    Acc2 acc;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         float ww = (i & 1) ? f[0] : 1 - f[0];
         ww *= (i & 2) ? f[1] : 1 - f[1];
         ww *= (i & 4) ? f[2] : 1 - f[2];
-        a0 = __fmaf_rn(ww, v[i].x, a0);
-        a1 = __fmaf_rn(ww, v[i].y, a1);
+        acc.fma(ww, v[i]);
     }
-    o0 = a0;
-    o1 = a1;
+    acc.get(o0, o1);
 }
 
 // host: sanerf_grid_t (C ABI) -> GridDev; also decides dense vs hashed per level exactly like the reference kernel

@@ -188,17 +188,15 @@ __device__ __forceinline__ void level_issue(const GridDev& g, int l, const float
 }
 
 __device__ __forceinline__ void level_finish(const LevelLoads& o, float& o0, float& o1) {
-    float a0 = 0.f, a1 = 0.f;
+    Acc2 acc;
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         float ww = (i & 1) ? o.f[0] : 1 - o.f[0];
         ww *= (i & 2) ? o.f[1] : 1 - o.f[1];
         ww *= (i & 4) ? o.f[2] : 1 - o.f[2];
-        a0 = __fmaf_rn(ww, o.v[i].x, a0);
-        a1 = __fmaf_rn(ww, o.v[i].y, a1);
+        acc.fma(ww, o.v[i]);
     }
-    o0 = a0;
-    o1 = a1;
+    acc.get(o0, o1);
 }
 
 // ---- x-paired gathers (SANERF_S2_XPAIR) ----------------------------------------------------------------------------------
@@ -244,16 +242,14 @@ __device__ __forceinline__ void pair_issue(const GridDev& g, int l, const float 
 // this lane's half of the trilinear blend (weights in the reference's product order (wx*wy)*wz, gridencoder.cu:170-195)
 __device__ __forceinline__ void pair_finish(const PairLoads& o, int xside, float& o0, float& o1) {
     const float wx = xside ? o.f[0] : 1 - o.f[0];
-    float a0 = 0.f, a1 = 0.f;
+    Acc2 acc;
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         float ww = wx * ((i & 1) ? o.f[1] : 1 - o.f[1]);
         ww *= (i & 2) ? o.f[2] : 1 - o.f[2];
-        a0 = __fmaf_rn(ww, o.v[i].x, a0);
-        a1 = __fmaf_rn(ww, o.v[i].y, a1);
+        acc.fma(ww, o.v[i]);
     }
-    o0 = a0;
-    o1 = a1;
+    acc.get(o0, o1);
 }
 
 // two points at once (two sample chunks of the same ray): twice the independent loads in flight per thread
