@@ -18,7 +18,11 @@ CSRC = os.path.join(HERE, "csrc")
 _VARIANT = os.environ.get("SANERF_LIB_VARIANT", "")
 LIBDIR = os.path.join(HERE, "lib_" + _VARIANT if _VARIANT else "lib")
 SO = os.path.join(LIBDIR, "libsanerf_b200.so")
-SOURCES = ["grid_encode.cu", "sh_encode.cu", "freq_encode.cu", "render.cu", "mlp_tc.cu", "heads.cu", "peer.cu"]
+# (source, object name, extra flags): render.cu is compiled twice -- the primary 16-warp flavour and the 20-warp flavour that only
+# carries the SAM-frame kernels (see the head of render.cu)
+SOURCES = [("grid_encode.cu", "grid_encode", []), ("sh_encode.cu", "sh_encode", []), ("freq_encode.cu", "freq_encode", []),
+           ("render.cu", "render", []), ("render.cu", "render_w20", ["-DSANERF_RENDER_FLAVOUR=20"]), ("mlp_tc.cu", "mlp_tc", []),
+           ("heads.cu", "heads", []), ("peer.cu", "peer", [])]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc.cuh"), os.path.join(CSRC, "grid_dev.cuh"), os.path.join(os.path.dirname(HERE), "include", "sanerf_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--threads", "2"] + os.environ.get("SANERF_NVCC_FLAGS", "").split()
@@ -40,14 +44,14 @@ def _stale(target, deps):
 
 def build(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
-    srcs = [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
-    objs = [os.path.join(LIBDIR, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    units = [(os.path.join(CSRC, s), os.path.join(LIBDIR, o + ".o"), fl) for s, o, fl in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+    objs = [o for _, o, _ in units]
     nvcc = _nvcc()
 
-    def compile_one(so):
-        s, o = so
+    def compile_one(unit):
+        s, o, fl = unit
         if force or _stale(o, [s] + HEADERS):
-            cmd = [nvcc] + NVCC_FLAGS + ["-c", s, "-o", o]
+            cmd = [nvcc] + NVCC_FLAGS + fl + ["-c", s, "-o", o]
             if verbose:
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
@@ -55,7 +59,7 @@ def build(force=False, verbose=False):
         return False
 
     with ThreadPoolExecutor(max_workers=4) as ex:
-        rebuilt = list(ex.map(compile_one, zip(srcs, objs)))
+        rebuilt = list(ex.map(compile_one, units))
     if any(rebuilt) or _stale(SO, objs):
         cmd = [nvcc, "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
         if verbose:

@@ -55,6 +55,21 @@ struct Acc2 {
     __device__ __forceinline__ void get(float& a0, float& a1) const { asm("mov.b64 {%0,%1}, %2;" : "=f"(a0), "=f"(a1) : "l"(bits)); }
 };
 
+// Packed pairs for code that runs the same scalar recipe on two independent items (the two sample chunks of a proposal round, the
+// two passes of the x-paired final stage): one issue slot per pair of results, each component the same IEEE operation as the
+// scalar code (add / sub / mul / fma .rn, add .rz).
+struct F2 {
+    unsigned long long b;
+    __device__ __forceinline__ F2() {}
+    __device__ __forceinline__ F2(float x, float y) { asm("mov.b64 %0, {%1,%2};" : "=l"(b) : "f"(x), "f"(y)); }
+    __device__ __forceinline__ float x() const { return __uint_as_float((uint32_t)b); }
+    __device__ __forceinline__ float y() const { return __uint_as_float((uint32_t)(b >> 32)); }
+};
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 m, F2 c) { F2 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r.b) : "l"(a.b), "l"(m.b), "l"(c.b)); return r; }
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 m) { F2 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.b) : "l"(a.b), "l"(m.b)); return r; }
+__device__ __forceinline__ F2 f2_sub(F2 a, F2 m) { F2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.b) : "l"(a.b), "l"(m.b)); return r; }
+__device__ __forceinline__ F2 f2_add_rz(F2 a, F2 m) { F2 r; asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r.b) : "l"(a.b), "l"(m.b)); return r; }
+
 // ---- C=8 feature grids: quarter-row gathers -------------------------------------------------------------------------
 // A C=8 row is 32 bytes.  "lane = sample, two LDG.128 per corner" costs 2 L1 tag cycles per distinct 128-byte line per
 // request (tools/l1_gather.cu), with up to 32 lines per request.  Here 4 lanes share a sample, each fetching 8 bytes (2 of

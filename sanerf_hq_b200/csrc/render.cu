@@ -29,11 +29,26 @@
 #include "grid_dev.cuh"
 #include "tc.cuh"
 
-namespace sanerf {
-
-#ifndef SANERF_RENDER_WARPS
-#define SANERF_RENDER_WARPS 16
+// This file is compiled twice (sanerf_hq_b200/build.py): the primary flavour (16 warps per CTA: rgb and object-head frames, the C
+// ABI entry points) and, with -DSANERF_RENDER_FLAVOUR=20, a second flavour with 20 warps per CTA that only instantiates the
+// kernels with the C=8 feature-grid gathers of the SAM frame, whose long gather chains want more warps to hide latency (measured
+// on the 800x800 SAM frame: 16 warps 18.85 ms, 20 warps 17.83, 24 warps 18.04; the rgb frame: 10.56 / 11.04 / 11.63).  Each
+// flavour lives in its own namespace, the primary one dispatches.
+#ifndef SANERF_RENDER_FLAVOUR
+#define SANERF_RENDER_FLAVOUR 16
 #endif
+#if SANERF_RENDER_FLAVOUR == 16
+#define SANERF_FLAVOUR_NS r16
+#else
+#define SANERF_FLAVOUR_NS r20
+#endif
+#ifndef SANERF_RENDER_WARPS
+#define SANERF_RENDER_WARPS SANERF_RENDER_FLAVOUR
+#endif
+
+namespace sanerf {
+namespace SANERF_FLAVOUR_NS {
+
 constexpr int kWarps = SANERF_RENDER_WARPS;   // warps (= rays in flight) per CTA; 4 warps = one tensor-core group
 constexpr int kGroups = kWarps / 4;
 #ifndef SANERF_S2_XPAIR
@@ -199,6 +214,76 @@ __device__ __forceinline__ void level_finish(const LevelLoads& o, float& o0, flo
     acc.get(o0, o1);
 }
 
+// The same for TWO points at once (the two sample chunks of a proposal round): the cell lookup and the corner weights are the
+// same scalar recipe on both, so they run as packed pairs (F2: FFMA2 / FADD2 / FMUL2, one issue slot per pair of results, each
+// component the IEEE operation of the scalar code); index arithmetic, clamps and loads stay per point.
+struct LevelLoads2 {
+    float2 va[8], vb[8];
+    F2 f[3];
+};
+
+__device__ __forceinline__ void cell_x2(const GridDev& g, int l, const float (&xa)[3], const float (&xb)[3], uint32_t (&b0a)[3], uint32_t (&b1a)[3],
+                                        uint32_t (&b0b)[3], uint32_t (&b1b)[3], F2 (&f)[3]) {
+    const uint32_t res = g.res[l];
+    const float resf = g.resf[l], top = g.topf[l];
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+        const F2 p = f2_fma(F2(xa[d], xb[d]), F2(resf, resf), F2(-0.5f, -0.5f));
+        const F2 pc(fminf(fmaxf(p.x(), 0.0f), top), fminf(fmaxf(p.y(), 0.0f), top));
+        const F2 t = f2_add_rz(pc, F2(8388608.0f, 8388608.0f));          // floor_split, both points
+        b0a[d] = __float_as_uint(t.x()) & 0x007fffffu;
+        b0b[d] = __float_as_uint(t.y()) & 0x007fffffu;
+        f[d] = f2_sub(pc, f2_sub(t, F2(8388608.0f, 8388608.0f)));
+        b1a[d] = min(b0a[d] + 1, res - 1);
+        b1b[d] = min(b0b[d] + 1, res - 1);
+    }
+}
+
+__device__ __forceinline__ void corner_loads(const GridDev& g, int l, const uint32_t (&b0)[3], const uint32_t (&b1)[3], float2 (&v)[8], const float2* smem0) {
+    const uint32_t res = g.res[l];
+    const uint32_t hmask = g.hmask[l];
+    const float2* __restrict__ rows = reinterpret_cast<const float2*>(g.base[l]);
+    if (hmask == 0) {
+        const uint32_t y0 = b0[1] * res, y1 = b1[1] * res, z0 = b0[2] * res * res, z1 = b1[2] * res * res;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t idx = ((i & 1) ? b1[0] : b0[0]) + ((i & 2) ? y1 : y0) + ((i & 4) ? z1 : z0);
+            v[i] = (SANERF_SMEM_L0 && smem0 && l == 0) ? smem0[idx] : __ldg(rows + idx);
+        }
+    } else {
+        const uint32_t x0 = b0[0] & hmask, x1 = b1[0] & hmask;
+        const uint32_t y0 = (b0[1] * 2654435761u) & hmask, y1 = (b1[1] * 2654435761u) & hmask;
+        const uint32_t z0 = (b0[2] * 805459861u) & hmask, z1 = (b1[2] * 805459861u) & hmask;
+#pragma unroll
+        for (int i = 0; i < 8; i++) v[i] = __ldg(rows + (((i & 1) ? x1 : x0) ^ ((i & 2) ? y1 : y0) ^ ((i & 4) ? z1 : z0)));
+    }
+}
+
+__device__ __forceinline__ void level_issue_x2(const GridDev& g, int l, const float (&xa)[3], const float (&xb)[3], LevelLoads2& o, const float2* smem0) {
+    uint32_t b0a[3], b1a[3], b0b[3], b1b[3];
+    cell_x2(g, l, xa, xb, b0a, b1a, b0b, b1b, o.f);
+    corner_loads(g, l, b0a, b1a, o.va, smem0);
+    corner_loads(g, l, b0b, b1b, o.vb, smem0);
+}
+
+__device__ __forceinline__ void level_finish_x2(const LevelLoads2& o, float& a0, float& a1, float& b0, float& b1) {
+    const F2 one(1.0f, 1.0f);
+    F2 nf[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) nf[d] = f2_sub(one, o.f[d]);
+    Acc2 acca, accb;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        F2 ww = (i & 1) ? o.f[0] : nf[0];
+        ww = f2_mul(ww, (i & 2) ? o.f[1] : nf[1]);
+        ww = f2_mul(ww, (i & 4) ? o.f[2] : nf[2]);
+        acca.fma(ww.x(), o.va[i]);
+        accb.fma(ww.y(), o.vb[i]);
+    }
+    acca.get(a0, a1);
+    accb.get(b0, b1);
+}
+
 // ---- x-paired gathers (SANERF_S2_XPAIR) ----------------------------------------------------------------------------------
 // Two adjacent lanes share one sample: the even lane fetches the four corners with x = x0, the odd lane those with x = x0+1.
 // The two x-neighbours of a (y,z) corner pair are adjacent table rows on the dense levels and on the hashed levels whenever x0
@@ -252,23 +337,72 @@ __device__ __forceinline__ void pair_finish(const PairLoads& o, int xside, float
     acc.get(o0, o1);
 }
 
+// both passes of the x-paired final stage at once (two samples per lane pair): packed cell lookup / weights like level_issue_x2
+struct PairLoads2 {
+    float2 va[4], vb[4];
+    F2 f[3];
+};
+
+__device__ __forceinline__ void pair_loads(const GridDev& g, int l, const uint32_t (&b0)[3], const uint32_t (&b1)[3], int xside, float2 (&v)[4],
+                                           const float2* smem0) {
+    const uint32_t res = g.res[l];
+    const uint32_t hmask = g.hmask[l];
+    const float2* __restrict__ rows = reinterpret_cast<const float2*>(g.base[l]);
+    const uint32_t bx = xside ? b1[0] : b0[0];
+    if (hmask == 0) {
+        const uint32_t y0 = b0[1] * res, y1 = b1[1] * res, z0 = b0[2] * res * res, z1 = b1[2] * res * res;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t idx = bx + ((i & 1) ? y1 : y0) + ((i & 2) ? z1 : z0);
+            v[i] = (SANERF_SMEM_L0 && smem0 && l == 0) ? smem0[idx] : __ldg(rows + idx);
+        }
+    } else {
+        const uint32_t xm = bx & hmask;
+        const uint32_t y0 = (b0[1] * 2654435761u) & hmask, y1 = (b1[1] * 2654435761u) & hmask;
+        const uint32_t z0 = (b0[2] * 805459861u) & hmask, z1 = (b1[2] * 805459861u) & hmask;
+#pragma unroll
+        for (int i = 0; i < 4; i++) v[i] = __ldg(rows + (xm ^ ((i & 1) ? y1 : y0) ^ ((i & 2) ? z1 : z0)));
+    }
+}
+
+__device__ __forceinline__ void pair_issue_x2(const GridDev& g, int l, const float (&xa)[3], const float (&xb)[3], int xside, PairLoads2& o,
+                                              const float2* smem0) {
+    uint32_t b0a[3], b1a[3], b0b[3], b1b[3];
+    cell_x2(g, l, xa, xb, b0a, b1a, b0b, b1b, o.f);
+    pair_loads(g, l, b0a, b1a, xside, o.va, smem0);
+    pair_loads(g, l, b0b, b1b, xside, o.vb, smem0);
+}
+
+__device__ __forceinline__ void pair_finish_x2(const PairLoads2& o, int xside, float& a0, float& a1, float& c0, float& c1) {
+    const F2 one(1.0f, 1.0f);
+    F2 nf[3];
+#pragma unroll
+    for (int d = 0; d < 3; d++) nf[d] = f2_sub(one, o.f[d]);
+    const F2 wx = xside ? o.f[0] : nf[0];
+    Acc2 acca, accb;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        F2 ww = f2_mul(wx, (i & 1) ? o.f[1] : nf[1]);
+        ww = f2_mul(ww, (i & 2) ? o.f[2] : nf[2]);
+        acca.fma(ww.x(), o.va[i]);
+        accb.fma(ww.y(), o.vb[i]);
+    }
+    acca.get(a0, a1);
+    accb.get(c0, c1);
+}
+
 // two points at once (two sample chunks of the same ray): twice the independent loads in flight per thread
 template <int L, int DEPTH>
 __device__ __forceinline__ void gather_levels_x2(const GridDev& g, const float (&xa)[3], const float (&xb)[3], bool ina, bool inb,
                                                  float (&fa)[2 * L], float (&fb)[2 * L], const float2* smem0) {
-    LevelLoads bufa[DEPTH], bufb[DEPTH];
+    LevelLoads2 buf[DEPTH];
 #pragma unroll
-    for (int d = 0; d < DEPTH && d < L; d++) {
-        level_issue(g, d, xa, bufa[d], smem0);
-        level_issue(g, d, xb, bufb[d], smem0);
-    }
+    for (int d = 0; d < DEPTH && d < L; d++) level_issue_x2(g, d, xa, xb, buf[d], smem0);
 #pragma unroll
     for (int l = 0; l < L; l++) {
         float a0, a1, b0, b1;
-        level_finish(bufa[l % DEPTH], a0, a1);
-        if (l + DEPTH < L) level_issue(g, l + DEPTH, xa, bufa[l % DEPTH]);
-        level_finish(bufb[l % DEPTH], b0, b1);
-        if (l + DEPTH < L) level_issue(g, l + DEPTH, xb, bufb[l % DEPTH]);
+        level_finish_x2(buf[l % DEPTH], a0, a1, b0, b1);
+        if (l + DEPTH < L) level_issue_x2(g, l + DEPTH, xa, xb, buf[l % DEPTH], nullptr);
         fa[2 * l] = ina ? a0 : 0.f;
         fa[2 * l + 1] = ina ? a1 : 0.f;
         fb[2 * l] = inb ? b0 : 0.f;
@@ -606,9 +740,10 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
     for (uint32_t base = blockIdx.x * kWarps; base < p.N; base += total_warps) {
         bool active = base + warp < p.N;
         uint32_t ray = active ? base + warp : p.N - 1;
-        if (p.tile_w) {   // the 16 warps take a 4x4-pixel tile of the row-major image instead of a 16-pixel row segment
-            const uint32_t tiles_x = p.tile_w >> 2, t = base / kWarps;
-            ray = (4 * (t / tiles_x) + (warp >> 2)) * p.tile_w + 4 * (t % tiles_x) + (warp & 3);
+        if (p.tile_w) {   // the warps take a 4 x (kWarps/4)-pixel tile of the row-major image instead of a row segment of kWarps pixels
+            constexpr uint32_t tw = kWarps / 4;
+            const uint32_t tiles_x = p.tile_w / tw, t = base / kWarps;
+            ray = (4 * (t / tiles_x) + (uint32_t)warp / tw) * p.tile_w + tw * (t % tiles_x) + (uint32_t)warp % tw;
             active = true;
         }
         // ---- ray setup: near/far from the AABB (renderer.py:122-139, 231-235) -------------------
@@ -702,11 +837,9 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
 #pragma unroll
                     for (int d = 0; d < 3; d++) px[q][d] = __shfl_sync(kFull, x01[d], 16 * q + (lane >> 1));
                 const int src = 2 * (lane & 15) + (lane >> 4);     // where this lane's own sample ends up (see below)
-                PairLoads pb[4];                                   // ring: unit u = 2 * level + pass lives in pb[u % 4]
-                pair_issue(p.grid, 0, px[0], xside, pb[0], pinned(2));
-                pair_issue(p.grid, 0, px[1], xside, pb[1], pinned(2));
-                pair_issue(p.grid, 1, px[0], xside, pb[2]);
-                pair_issue(p.grid, 1, px[1], xside, pb[3]);
+                PairLoads2 pp[2];                                  // ring: level l (both passes) lives in pp[l % 2]
+                pair_issue_x2(p.grid, 0, px[0], px[1], xside, pp[0], pinned(2));
+                pair_issue_x2(p.grid, 1, px[0], px[1], xside, pp[1], nullptr);
 #pragma unroll 1
                 for (int lb = 0; lb < GKP / 8; lb++) {
                     uint32_t hi[4], lo[4];
@@ -716,10 +849,8 @@ __global__ void __launch_bounds__(kThreads, 1) render_kernel(const __grid_consta
                         float o0 = 0.f, o1 = 0.f;
                         if (l < GL) {                  // uniform
                             float a0, a1, c0, c1;
-                            pair_finish(pb[(2 * j) % 4], xside, a0, a1);
-                            if (l + 2 < GL) pair_issue(p.grid, l + 2, px[0], xside, pb[(2 * j) % 4]);
-                            pair_finish(pb[(2 * j + 1) % 4], xside, c0, c1);
-                            if (l + 2 < GL) pair_issue(p.grid, l + 2, px[1], xside, pb[(2 * j + 1) % 4]);
+                            pair_finish_x2(pp[j % 2], xside, a0, a1, c0, c1);
+                            if (l + 2 < GL) pair_issue_x2(p.grid, l + 2, px[0], px[1], xside, pp[j % 2], nullptr);
                             // both halves of a sample -> both lanes of its pair; then the even lane of pair k offers sample k
                             // (pass 0) and the odd lane sample 16 + k (pass 1), and every lane fetches its own sample
                             a0 += __shfl_xor_sync(kFull, a0, 1);
@@ -1018,6 +1149,7 @@ static int launch_render(const RenderParams& p, bool sam, bool mask, uint32_t ma
         cudaFuncSetAttribute(kfn, cudaFuncAttributePreferredSharedMemoryCarveout, (int)((smem + 2048) * 100 / (228 * 1024)) + 1); \
         kfn<<<blocks, kThreads, smem, st>>>(p);                                                                 \
     } while (0)
+#if SANERF_RENDER_FLAVOUR == 16
     if constexpr (PERTURB) {   // perturbed sampling is instantiated for the rgb / object-head frames (trainer.py:513, 1308)
         if (sam) return SANERF_E_CONFIG;
         if (mask) SANERF_LAUNCH(false, true);
@@ -1028,17 +1160,18 @@ static int launch_render(const RenderParams& p, bool sam, bool mask, uint32_t ma
         else if (mask) SANERF_LAUNCH(false, true);
         else SANERF_LAUNCH(false, false);
     }
+#else      // the 20-warp flavour only carries the kernels with the feature-grid gathers
+    static_assert(!PERTURB, "flavour 20: SAM frames only");
+    if (sam && mask) SANERF_LAUNCH(true, true);
+    else if (sam) SANERF_LAUNCH(true, false);
+    else return SANERF_E_CONFIG;
+#endif
 #undef SANERF_LAUNCH
     return check_launch();
 }
 
-}  // namespace sanerf
-
-using namespace sanerf;
-
-extern "C" {
-
-int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf_stream_t stream) {
+// sanerf_render for this flavour: host structs -> RenderParams -> launch
+int render_entry(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf_stream_t stream) {
     if (!m || !a) return SANERF_E_NULL;
     if (a->N == 0) return 0;
     if (!a->image || !a->depth || !a->weights_sum || !m->u65 || !m->u33) return SANERF_E_NULL;
@@ -1081,7 +1214,7 @@ int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf
     p.image = a->image; p.depth = a->depth; p.wsum = a->weights_sum;
     p.sam_in = a->sam_in; p.mask_in = a->mask_in; p.mask_tiled = a->mask_in_tiled;
     p.cam_w = a->cam_w; p.cam_ray0 = a->cam_ray0; p.image_u8 = a->image_u8;
-    p.tile_w = (kWarps == 16 && a->tile_w && a->tile_w % 4 == 0 && a->N % (4 * a->tile_w) == 0) ? a->tile_w : 0;
+    p.tile_w = (kWarps % 4 == 0 && a->tile_w && a->tile_w % (kWarps / 4) == 0 && a->N % (4 * a->tile_w) == 0) ? a->tile_w : 0;
     for (int i = 0; i < 4; i++) p.cam_intr[i] = a->cam_intrinsics[i];
     for (int i = 0; i < 12; i++) p.cam_pose[i] = a->cam_pose[i];
     p.n_peer = a->n_peer_out;
@@ -1101,12 +1234,37 @@ int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf
     const bool perturb = a->noise0 || a->noise1 || a->noise2;
     if (perturb && !(a->noise0 && a->noise1 && a->noise2)) return SANERF_E_NULL;
     p.noise[0] = a->noise0; p.noise[1] = a->noise1; p.noise[2] = a->noise2;
+#if SANERF_RENDER_FLAVOUR == 16
     if (PL == 5 && GL == 16 && m->grid_hidden == 64 && m->view_hidden == 32)
         return perturb ? launch_render<5, 16, 64, 32, true>(p, sam, mask, a->max_ctas, st) : launch_render<5, 16, 64, 32, false>(p, sam, mask, a->max_ctas, st);
     if (PL == 4 && GL == 4 && m->grid_hidden == 16 && m->view_hidden == 16)
         return perturb ? launch_render<4, 4, 16, 16, true>(p, sam, mask, a->max_ctas, st) : launch_render<4, 4, 16, 16, false>(p, sam, mask, a->max_ctas, st);
+#else
+    if (PL == 5 && GL == 16 && m->grid_hidden == 64 && m->view_hidden == 32 && sam && !perturb)
+        return launch_render<5, 16, 64, 32, false>(p, sam, mask, a->max_ctas, st);
+#endif
     return SANERF_E_CONFIG;
 }
+
+}  // namespace SANERF_FLAVOUR_NS
+}  // namespace sanerf
+
+#if SANERF_RENDER_FLAVOUR == 16
+namespace sanerf { namespace r20 { int render_entry(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf_stream_t stream); } }
+using namespace sanerf;
+using namespace sanerf::r16;
+
+extern "C" {
+
+int sanerf_render(const sanerf_model_t* m, const sanerf_render_args_t* a, sanerf_stream_t stream) {
+    if (!m || !a) return SANERF_E_NULL;
+    // the SAM frame of the default network runs in the 20-warp flavour
+    const bool perturb = a->noise0 || a->noise1 || a->noise2;
+    if (a->sam_in && !perturb && m->prop_grid[0].num_levels == 5 && m->grid.num_levels == 16 && m->grid_hidden == 64 && m->view_hidden == 32)
+        return sanerf::r20::render_entry(m, a, stream);
+    return sanerf::r16::render_entry(m, a, stream);
+}
+
 
 size_t sanerf_render_workspace_bytes(void) { return SANERF_RENDER_WORKSPACE_BYTES; }
 
@@ -1137,3 +1295,4 @@ const char* sanerf_error_string(int code) {
 }
 
 }  // extern "C"
+#endif  // primary flavour
