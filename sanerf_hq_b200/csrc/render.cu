@@ -638,22 +638,32 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, int
     const GridDev& g = p.prop[e];
     const float* w0 = sm + S::prop_w0 + e * 2 * 16 * S::PKP;  // hi image; lo image follows
     const float* w1 = sm + S::prop_w1 + e * 16;
-    // two chunks of 32 samples per iteration: twice the gather loads in flight, and ONE tensor-core round for both
+    // two chunks of 32 samples per iteration: twice the gather loads in flight, and ONE tensor-core round for both.
+    // Exact early-out behind an opaque surface: once the delta*sigma of the samples in front sums to more than 105, the
+    // transmittance exp(-sum) of every later sample is exactly 0 in fp32 (e^-104 already rounds to 0), so its weight
+    // alpha * 0 is exactly 0 whatever its density (a NaN is scrubbed to 0 as well, renderer.py:325): the later chunks need no
+    // position, no gather and no density -- delta*sigma = 0 gives the same zeros.  The warp still takes part in the group's
+    // tensor-core round (with zero rows).  Trained scenes hit this on most rays; the uniform fog of the benchmark never does.
+    float in_front = 0.f;
 #pragma unroll 1
     for (int i = 0; i < T / 64; i++) {
         const int ja = lane + 64 * i, jb = ja + 32;
-        float tmid, da, db, xa[3], xb[3];
-        const float inv_t = 1.0f / (float)T;   // bins == nullptr: linspace(0,1,T+1) (renderer.py:262-266; j/T is exact)
-        const bool ina = sample_point(r, bins ? bins[ja] : (float)ja * inv_t, bins ? bins[ja + 1] : (float)(ja + 1) * inv_t, tmid, da, xa);
-        const bool inb = sample_point(r, bins ? bins[jb] : (float)jb * inv_t, bins ? bins[jb + 1] : (float)(jb + 1) * inv_t, tmid, db, xb);
+        const bool dead = in_front > 105.0f;      // warp-uniform
+        float da = 0.f, db = 0.f;
         float feata[S::PKP], featb[S::PKP];
-        {
+#pragma unroll
+        for (int k = 0; k < S::PKP; k++) feata[k] = featb[k] = 0.f;
+        if (!dead) {
+            float tmid, xa[3], xb[3];
+            const float inv_t = 1.0f / (float)T;   // bins == nullptr: linspace(0,1,T+1) (renderer.py:262-266; j/T is exact)
+            const bool ina = sample_point(r, bins ? bins[ja] : (float)ja * inv_t, bins ? bins[ja + 1] : (float)(ja + 1) * inv_t, tmid, da, xa);
+            const bool inb = sample_point(r, bins ? bins[jb] : (float)jb * inv_t, bins ? bins[jb + 1] : (float)(jb + 1) * inv_t, tmid, db, xb);
             float fa[2 * PL], fb[2 * PL];
             gather_levels_x2<PL, SANERF_PROP_DEPTH>(g, xa, xb, ina, inb, fa, fb, smem0);
 #pragma unroll
-            for (int k = 0; k < S::PKP; k++) {
-                feata[k] = k < 2 * PL ? fa[k] : 0.f;
-                featb[k] = k < 2 * PL ? fb[k] : 0.f;
+            for (int k = 0; k < 2 * PL; k++) {
+                feata[k] = fa[k];
+                featb[k] = fb[k];
             }
         }
         // prop_mlp layer 0 (2L -> 16, ReLU; network.py:137,142) on the tensor core: 4 warps x 32 samples = one 128-row MMA tile per chunk
@@ -670,8 +680,11 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, int
             ob = __fmaf_rn(w.x, hb[k], ob); ob = __fmaf_rn(w.y, hb[k + 1], ob);
             ob = __fmaf_rn(w.z, hb[k + 2], ob); ob = __fmaf_rn(w.w, hb[k + 3], ob);
         }
-        ds[ja] = __fmul_rn(da, expf(oa));                   // trunc_exp fwd (activation.py:10); renderer.py:310
-        ds[jb] = __fmul_rn(db, expf(ob));
+        const float dsa = dead ? 0.f : __fmul_rn(da, expf(oa));   // trunc_exp fwd (activation.py:10); renderer.py:310
+        const float dsb = dead ? 0.f : __fmul_rn(db, expf(ob));
+        ds[ja] = dsa;
+        ds[jb] = dsb;
+        if (i + 1 < T / 64) in_front += warp_sum(dsa + dsb);
     }
     __syncwarp();
 }

@@ -384,3 +384,28 @@ def test_head_training_on_frozen_geometry_runs_the_fused_kernel(mode):
     # with a trainable geometry parameter the call must fall back to the fully differentiable path
     model.grid_mlp.net[0].weight.requires_grad = True
     assert not model._can_train_heads_on_fused_geometry(rays_o, dict(kw, perturb=False))
+
+
+def test_exact_early_out_behind_opaque_samples():
+    """The proposal stage skips positions / gathers / density of sample chunks whose transmittance is exactly 0 in fp32 (the
+    delta*sigma in front sums to > 105): their weights are exactly 0 either way.  A proposal network with a steep density makes
+    most rays opaque within the first 64 coarse samples; every output and both sample_pdf index buffers must still match the
+    oracle, which evaluates everything."""
+    opt, params, specs = make_case()
+    params = {k: v.clone() for k, v in params.items()}
+    params["prop_mlp.0.net.1.weight"] *= 100.0        # ~half of the rays become opaque within the first 64 coarse samples
+    model = build_model(opt, params)
+    rays_o, rays_d = frame_rays(800, 800, pose_k=8, rows=(380, 396), cols=(300, 332))   # 512 rays
+    ref, ex = O.run(params, specs, opt, rays_o, rays_d)
+    ds0 = (ex["real_bins"][0][:, 1:] - ex["real_bins"][0][:, :-1]) * ex["sigmas"][0]
+    opaque_early = (ds0[:, :64].sum(-1) > 105).float().mean().item()
+    assert opaque_early > 0.2, f"the test scene must exercise the early-out ({opaque_early:.2f} of the rays do)"
+    taps = dict(inds0=None, inds1=None, weights2=None, bins2=None)
+    out = _render(model, rays_o, rays_d, False, True, taps=taps)
+    for k, v in ref.items():
+        assert_close(out[k], v, REL_TOL, f"early-out/{k}")
+    assert_close(taps["bins2"], ex["bins"][2], REL_TOL, "early-out/bins2")
+    for i, name in enumerate(("inds0", "inds1")):
+        aux = ex["pdf"][i]
+        n_bad, n_unexpl = index_mismatch_report(taps[name].cpu().numpy(), aux["inds"].numpy(), aux["cdf"].numpy(), aux["u"].numpy())
+        assert n_unexpl == 0, (name, n_bad, n_unexpl)
