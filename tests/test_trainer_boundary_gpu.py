@@ -177,3 +177,45 @@ def test_object_stage_freezing_train_step_and_checkpoint_roundtrip():
         assert list(sd_ref) == list(sd_new)
         for k in sd_ref:
             assert torch.equal(sd_ref[k], sd_new[k]), k
+
+
+def test_train_step_timing_report():
+    """Whole optimizer steps of the reference's Trainer (train_step + backward + post_train_step + Adam) over the reference model
+    (its CUDA kernels + cuBLAS) and over the drop-in model, 4096 rays: rgb stage (composed path on this repo's encoder kernels)
+    and object stage (fused geometry + differentiable head).  Report -> gpurun_out/train_step_timing.json; the assertion is only
+    a guard against a gross regression."""
+    import json
+    R = _R()
+    report = {}
+    for stage in ("rgb", "object"):
+        obj = stage == "object"
+        opt = TH.trainer_opt(with_mask=obj, num_rays=4096, adaptive_num_rays=False)
+        _, ref, cand = _pair(opt, seed=31)
+        data = [TH.train_data(4096, DEV, seed=s, masks=obj) for s in range(4)]
+        with tempfile.TemporaryDirectory() as ws:
+            for name, model in (("reference", ref), ("candidate", cand)):
+                if obj:                                                          # main.py:253-256 by name
+                    for k, v in model.named_parameters():
+                        v.requires_grad = k.startswith(("m_grid", "mask_mlp"))
+                tr = TH.make_trainer(R, "cuda", model, opt, os.path.join(ws, name))
+                with R.env("cuda"):
+                    for i in range(3):
+                        TH.one_optimizer_step(tr, data[i % 4])
+                    torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
+                    for i in range(10):
+                        _, _, loss = TH.one_optimizer_step(tr, data[i % 4])
+                    e1.record()
+                    torch.cuda.synchronize()
+                assert torch.isfinite(loss)
+                report.setdefault(stage, {})[name + "_ms_per_step"] = e0.elapsed_time(e1) / 10
+        r = report[stage]
+        r["speedup"] = r["reference_ms_per_step"] / r["candidate_ms_per_step"]
+        r["rays"] = 4096
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/train_step_timing.json", "w") as f:
+        json.dump(report, f, indent=1)
+    print(json.dumps(report))
+    for stage, r in report.items():
+        assert r["candidate_ms_per_step"] <= 2.0 * r["reference_ms_per_step"], (stage, r)
