@@ -58,6 +58,14 @@ constexpr int kGroups = kWarps / 4;
 #define SANERF_SMEM_L0 3    // bit mask of level-0 tables pinned in shared memory (1 prop0, 2 prop1, 4 grid).  800x800 RGB frame:
                             // none 11.07 ms, prop0 11.06, prop0+prop1 10.97, all three 11.06 (L1 shrinks from 164 to 68 KB)
 #endif
+#ifndef SANERF_PROP_MLP_CC
+#define SANERF_PROP_MLP_CC 0   // 1 / 2: first layer of the proposal MLPs on the FMA pipe instead of the tensor core (packed FFMA2 over the two
+                               // chunks; 1 = accumulated level by level between the gathers (128 registers, spills), 2 = after the gathers):
+                               // no tensor-core round, no group synchronisation and no TMEM slot in the proposal stages.  Measured (same
+                               // box, 800x800 RGB frame; tensor-core path 10.69 ms): variant 2 at 16 warps 10.97, at 20 warps 10.55, at 24
+                               // warps 11.23; SAM frame at 20 warps 17.91 vs 17.83.  The tensor-core round is the better trade at 16 warps
+                               // and +-1 % elsewhere -- not adopted.
+#endif
 #ifndef SANERF_PROP_DEPTH
 #define SANERF_PROP_DEPTH 1   // levels of loads in flight per chunk in the proposal gathers (1: 11.90 ms, 2: 11.99 ms)
 #endif
@@ -410,6 +418,39 @@ __device__ __forceinline__ void gather_levels_x2(const GridDev& g, const float (
     }
 }
 
+// The same gathers with the first proposal-MLP layer (2L -> 16, network.py:137,142) folded in: as soon as a level's two
+// features are blended they are multiplied into the 16 hidden units of both chunks (h[n] = {chunk a, chunk b}, one FFMA2 per
+// unit and feature with the weight as the broadcast scalar) -- the 32 FMAs of a level run while the next level's loads are in
+// flight, the features never wait in registers, and the proposal stages need no tensor-core round.  w: [2L][16] fp32 in shared
+// memory (every lane reads the same float4: broadcast).  fp32 FMA chain over k = 0..2L-1, like a cuBLAS dot product.
+template <int L, int DEPTH>
+__device__ __forceinline__ void gather_levels_x2_mlp(const GridDev& g, const float (&xa)[3], const float (&xb)[3], bool ina, bool inb,
+                                                     const float* __restrict__ w, F2 (&h)[16], const float2* smem0) {
+    LevelLoads2 buf[DEPTH];
+#pragma unroll
+    for (int d = 0; d < DEPTH && d < L; d++) level_issue_x2(g, d, xa, xb, buf[d], smem0);
+#pragma unroll
+    for (int l = 0; l < L; l++) {
+        float a0, a1, b0, b1;
+        level_finish_x2(buf[l % DEPTH], a0, a1, b0, b1);
+        if (l + DEPTH < L) level_issue_x2(g, l + DEPTH, xa, xb, buf[l % DEPTH], nullptr);
+        const F2 f0(ina ? a0 : 0.f, inb ? b0 : 0.f), f1(ina ? a1 : 0.f, inb ? b1 : 0.f);
+#pragma unroll
+        for (int n = 0; n < 16; n += 4) {
+            const float4 u = *reinterpret_cast<const float4*>(w + (2 * l) * 16 + n);
+            const float4 v = *reinterpret_cast<const float4*>(w + (2 * l + 1) * 16 + n);
+            h[n] = f2_fma(F2(u.x, u.x), f0, h[n]);
+            h[n + 1] = f2_fma(F2(u.y, u.y), f0, h[n + 1]);
+            h[n + 2] = f2_fma(F2(u.z, u.z), f0, h[n + 2]);
+            h[n + 3] = f2_fma(F2(u.w, u.w), f0, h[n + 3]);
+            h[n] = f2_fma(F2(v.x, v.x), f1, h[n]);
+            h[n + 1] = f2_fma(F2(v.y, v.y), f1, h[n + 1]);
+            h[n + 2] = f2_fma(F2(v.z, v.z), f1, h[n + 2]);
+            h[n + 3] = f2_fma(F2(v.w, v.w), f1, h[n + 3]);
+        }
+    }
+}
+
 // y[n] = sum_k W[n][k] x[k], W in shared memory as [N][KP] (KP = K rounded up to 4, zero padded);
 // every lane reads the same address (broadcast LDS.128), activations stay in registers.
 template <int K, int KP, int N, bool RELU>
@@ -474,9 +515,16 @@ template <int PL, int GL, int HG, int HV>
 __global__ void __launch_bounds__(kThreads) render_prepare_kernel(const __grid_constant__ RenderParams p, float* __restrict__ sm) {
     using S = Smem<PL, GL, HG>;
     const int tid = threadIdx.x;
+#if SANERF_PROP_MLP_CC
+    for (int i = tid; i < 2 * S::PK * 16; i += kThreads) {   // [net][k][16] fp32 (gather_levels_x2_mlp)
+        const int e = i / (S::PK * 16), k = (i / 16) % S::PK, n = i % 16;
+        sm[S::prop_w0 + i] = __ldg(p.prop_w0[e] + n * S::PK + k);
+    }
+#else
     for (int e = 0; e < 2; e++)
         tc::stage_split_weights<16, S::PK, S::PKP>(sm + S::prop_w0 + e * 2 * 16 * S::PKP, sm + S::prop_w0 + (e * 2 + 1) * 16 * S::PKP,
                                                    p.prop_w0[e], tid, kThreads);
+#endif
     for (int i = tid; i < 32; i += kThreads) sm[S::prop_w1 + i] = __ldg(p.prop_w1[i / 16] + (i % 16));
     {
         __nv_bfloat16* w0 = reinterpret_cast<__nv_bfloat16*>(sm + S::grid_w0);
@@ -650,6 +698,68 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, int
         const int ja = lane + 64 * i, jb = ja + 32;
         const bool dead = in_front > 105.0f;      // warp-uniform
         float da = 0.f, db = 0.f;
+#if SANERF_PROP_MLP_CC
+        if (dead) {
+            ds[ja] = 0.f;
+            ds[jb] = 0.f;
+            continue;
+        }
+        float oa, ob;
+        {
+            float tmid, xa[3], xb[3];
+            const float inv_t = 1.0f / (float)T;
+            const bool ina = sample_point(r, bins ? bins[ja] : (float)ja * inv_t, bins ? bins[ja + 1] : (float)(ja + 1) * inv_t, tmid, da, xa);
+            const bool inb = sample_point(r, bins ? bins[jb] : (float)jb * inv_t, bins ? bins[jb + 1] : (float)(jb + 1) * inv_t, tmid, db, xb);
+            const float* wcc = sm + S::prop_w0 + e * S::PK * 16;
+            F2 o(0.f, 0.f);                        // 16 -> 1 (network.py:138,143), ReLU on the way in
+#if SANERF_PROP_MLP_CC == 1
+            F2 h[16];
+#pragma unroll
+            for (int n = 0; n < 16; n++) h[n] = F2(0.f, 0.f);
+            gather_levels_x2_mlp<PL, SANERF_PROP_DEPTH>(g, xa, xb, ina, inb, wcc, h, smem0);
+#pragma unroll
+            for (int k = 0; k < 16; k += 4) {
+                const float4 w = *reinterpret_cast<const float4*>(w1 + k);
+                o = f2_fma(F2(w.x, w.x), F2(fmaxf(h[k].x(), 0.f), fmaxf(h[k].y(), 0.f)), o);
+                o = f2_fma(F2(w.y, w.y), F2(fmaxf(h[k + 1].x(), 0.f), fmaxf(h[k + 1].y(), 0.f)), o);
+                o = f2_fma(F2(w.z, w.z), F2(fmaxf(h[k + 2].x(), 0.f), fmaxf(h[k + 2].y(), 0.f)), o);
+                o = f2_fma(F2(w.w, w.w), F2(fmaxf(h[k + 3].x(), 0.f), fmaxf(h[k + 3].y(), 0.f)), o);
+            }
+#else
+            // features first, then eight hidden units at a time: h[n] = {chunk a, chunk b}, one FFMA2 per unit and feature with the
+            // weight as the broadcast scalar (every lane reads the same float4 of the [2L][16] fp32 image)
+            float fa[2 * PL], fb[2 * PL];
+            gather_levels_x2<PL, SANERF_PROP_DEPTH>(g, xa, xb, ina, inb, fa, fb, smem0);
+#pragma unroll
+            for (int n0 = 0; n0 < 16; n0 += 8) {
+                F2 h[8];
+#pragma unroll
+                for (int n = 0; n < 8; n++) h[n] = F2(0.f, 0.f);
+#pragma unroll
+                for (int k = 0; k < 2 * PL; k++) {
+                    const F2 f(fa[k], fb[k]);
+                    const float4 u = *reinterpret_cast<const float4*>(wcc + k * 16 + n0);
+                    const float4 v = *reinterpret_cast<const float4*>(wcc + k * 16 + n0 + 4);
+                    h[0] = f2_fma(F2(u.x, u.x), f, h[0]);
+                    h[1] = f2_fma(F2(u.y, u.y), f, h[1]);
+                    h[2] = f2_fma(F2(u.z, u.z), f, h[2]);
+                    h[3] = f2_fma(F2(u.w, u.w), f, h[3]);
+                    h[4] = f2_fma(F2(v.x, v.x), f, h[4]);
+                    h[5] = f2_fma(F2(v.y, v.y), f, h[5]);
+                    h[6] = f2_fma(F2(v.z, v.z), f, h[6]);
+                    h[7] = f2_fma(F2(v.w, v.w), f, h[7]);
+                }
+#pragma unroll
+                for (int n = 0; n < 8; n++) {
+                    const float w = w1[n0 + n];
+                    o = f2_fma(F2(w, w), F2(fmaxf(h[n].x(), 0.f), fmaxf(h[n].y(), 0.f)), o);
+                }
+            }
+#endif
+            oa = o.x();
+            ob = o.y();
+        }
+#else
         float feata[S::PKP], featb[S::PKP];
 #pragma unroll
         for (int k = 0; k < S::PKP; k++) feata[k] = featb[k] = 0.f;
@@ -680,6 +790,7 @@ __device__ __forceinline__ void proposal_stage(const RenderParams& p, int e, int
             ob = __fmaf_rn(w.x, hb[k], ob); ob = __fmaf_rn(w.y, hb[k + 1], ob);
             ob = __fmaf_rn(w.z, hb[k + 2], ob); ob = __fmaf_rn(w.w, hb[k + 3], ob);
         }
+#endif
         const float dsa = dead ? 0.f : __fmul_rn(da, expf(oa));   // trunc_exp fwd (activation.py:10); renderer.py:310
         const float dsb = dead ? 0.f : __fmul_rn(db, expf(ob));
         ds[ja] = dsa;
