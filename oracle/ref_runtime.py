@@ -9,6 +9,10 @@ Two backends for the CUDA-only pybind modules that gridencoder/grid.py:9-12 and 
   "cpu"   fake modules backed by the C restatement (oracle/sanerf_oracle.c)  -> the reference's Python on the host cores
           (the reference has no CPU encoder); used by bench.py --impl reference.
 
+  "native" the reference's Python over THIS REPO's kernels through the pybind-compatible modules of
+          sanerf_hq_b200/native_backend.py -> the B-native boundary test: the reference's own GridEncoder /
+          SHEncoder / NeRFNetwork / renderer, unmodified, on libsanerf_b200.
+
 The reference's top-level module names (nerf.renderer, encoding, activation, gridencoder, shencoder, freqencoder) are the
 same as this repo's drop-in shims, so the reference is imported inside `env()`, a context manager that swaps those names in
 sys.modules / sys.path in and out.  Everything that may trigger an import inside the reference (model construction:
@@ -69,6 +73,9 @@ def available(backend="cuda"):
     ok = os.path.exists(os.path.join(PYC, "nerf", "renderer" + EXT)) and os.path.exists(os.path.join(PYC, "encoding" + EXT))
     if backend == "cuda":
         ok = ok and all(os.path.exists(os.path.join(REFDIR, n + ".so")) for n in ("_gridencoder", "_shencoder"))
+    if backend == "native":
+        from sanerf_hq_b200 import _lib
+        ok = ok and os.path.exists(_lib.lib_path())
     return ok
 
 
@@ -158,6 +165,9 @@ def _stub_modules(backend):
         sh = types.ModuleType("_shencoder")
         sh.sh_encode_forward = lambda inputs, outputs, B, D, C, dy_dx: K.sh_encode_forward(inputs, B, C, outputs=outputs)
         mods["_gridencoder"], mods["_shencoder"] = ge, sh
+    if backend == "native":
+        from sanerf_hq_b200 import native_backend
+        mods.update(native_backend.modules())
     return mods
 
 
