@@ -1,7 +1,6 @@
 """GPU: the encoder operators of libsanerf_b200 (through the C ABI, via the drop-in nn.Modules) vs the CPU
 oracle (oracle/sanerf_oracle.c), on seeded inputs.  Bit-exact where the arithmetic is the same FMA
 sequence (grid forward), tight fp32 tolerance elsewhere (stated per test)."""
-import ctypes
 
 import numpy as np
 import pytest

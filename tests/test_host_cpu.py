@@ -6,7 +6,6 @@ import subprocess
 import sys
 import tempfile
 
-import numpy as np
 import pytest
 import torch
 

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import REPO, O
+from helpers import REPO
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
