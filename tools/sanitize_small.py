@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Small renders of every fused variant for compute-sanitizer (run under `compute-sanitizer --tool memcheck|racecheck`):
-default-size networks, 96 rays, rgb / rgb perturbed / SAM feature (NHWC, NCHW + resize) / object head / frozen-geometry training."""
+default-size networks, 96 rays, rgb / rgb perturbed / rgb with early-out rays / SAM feature (NHWC, NCHW + resize) / object head / frozen-geometry training."""
 import os
 import sys
 
@@ -19,6 +19,10 @@ for wl in ("rgb", "sam", "mask"):
             model.render(ro, rd, staged=True, perturb=False)
             model.render(ro, rd, staged=True, perturb=True)
             model.render_image(orbit_pose(1), lego_intrinsics(8, 12), 8, 12, return_uint8=True)
+            # a steep-density scene: most rays turn opaque inside the first 64 coarse samples -> the exact early-out of the proposal stage
+            model.prop_mlp[0].net[1].weight.mul_(100.0)
+            model.render(ro, rd, staged=True, perturb=False)
+            model.prop_mlp[0].net[1].weight.div_(100.0)
         elif wl == "sam":
             model.render(ro, rd, staged=False, perturb=False, return_feats=1, H=8, W=12)
             model.render(ro, rd, staged=False, perturb=False, return_feats=1, H=8, W=12, feature_layout="nchw", feature_size=(5, 7))
