@@ -9,7 +9,7 @@ samples 128+64+32) of a different pose of a seeded 24-pose orbit, through this r
 launch of the fused sm_100a kernel (+ one tensor-core head launch for the SAM-feature / object workloads).
 
 The JSON line (rank 0) is the headline workload (`--workload`, default rgb = config #2); unless `--only` is given it also
-carries `workloads: {sam: {...}, mask: {...}}` = BASELINE configs #3 / #4 measured the same way, and at N = 8 `config5` = the
+carries `workloads: {sam: {...}, mask: {...}}` = BASELINE configs #3 / #4 measured the same way, and at N = 8 (and N = 1) `config5` = the
 1600x1600 RGB+SAM frame sharded `rank r <- rows [200r, 200r+200)` with a bit-for-bit check against the 1-GPU frame.
 
 Per workload: value = whole-job Mrays/s with rays resident in HBM; e2e = the same through the public API with HOST (pinned)
@@ -66,6 +66,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ref-gpu", action="store_true")
     ap.add_argument("--no-l2-flush", action="store_true")
+    ap.add_argument("--no-config5", action="store_true", help="N = 1: skip the single-GPU 1600x1600 frame of BASELINE config 5")
     return ap.parse_args()
 
 
@@ -305,7 +306,7 @@ def result_spec(wl):
     return spec
 
 
-def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, steps=None, warmup=None, tag=None):
+def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, steps=None, warmup=None, tag=None, baselines=True):
     """All numbers of one workload on this rank's `H x W` rays.  Default (weak scaling): every rank renders its own view of the
     orbit, H x W pixels; with `rows_of_rank` / `global_h` (strong scaling): rows `rows_of_rank` of ONE `global_h` x W frame.
     Returns a dict on rank 0."""
@@ -543,10 +544,10 @@ def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, ste
         }
         if sampler:
             res["clocks"] = sampler.summary()
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and baselines and not args.no_cpu_baseline:
             mr, cores, kind, sample, _ = cpu_baseline(wl, model.state_dict(), (40 if wl == "rgb" else 12) if headline else 8, H, W)
             res["cpu_baseline"] = {"value": mr, "unit": "Mrays/s", "cores": cores, "kind": kind, "sample": sample}
-        if world == 1 and not args.no_ref_gpu and not args.only:
+        if world == 1 and baselines and not args.no_ref_gpu and not args.only:
             try:
                 res["ref_gpu_baseline"] = ref_gpu_baseline(wl, model, dev, H, W, poses, intr, out0)
                 best = res["ref_gpu_baseline"].get("max_ray_batch_4096") or res["ref_gpu_baseline"].get("rows_5_per_call_4000_rays")
@@ -569,7 +570,7 @@ def config5(args, ctx):
     Hg = Wg = 1600
     rows = Hg // world
     res = measure("sam", args, ctx, rows, Wg, headline=False, rows_of_rank=(rank * rows, (rank + 1) * rows), global_h=Hg,
-                  steps=min(args.steps, 10), warmup=3, tag="config5 sam (strong-sharded 1600x1600)")
+                  steps=min(args.steps, 10), warmup=3, tag="config5 sam (strong-sharded 1600x1600)", baselines=False)
     model, got = ctx.pop("last_model"), ctx.pop("last_out0")
     equal = {}
     if rank == 0:
@@ -628,6 +629,14 @@ def main():
                 torch.cuda.empty_cache()
         if world == 8 and H == H_FRAME and W == W_FRAME:
             extra["config5"] = config5(args, ctx)
+        elif world == 1 and H == H_FRAME and W == W_FRAME and not args.no_config5:
+            # the same 1600x1600 frame on ONE GPU: the denominator of config 5's strong scaling.  No collective is involved at
+            # N = 1, so a failure here (e.g. a smaller GPU running out of memory) must not cost the headline line.
+            try:
+                extra["config5"] = config5(args, ctx)
+            except Exception as e:   # noqa: BLE001
+                extra["config5"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+                torch.cuda.empty_cache()
 
     if rank == 0:
         line = {"metric": METRIC, "value": head["value"], "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
