@@ -487,6 +487,29 @@ def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, ste
             cam_ms = timed_loop(step_cam, steps, warmup)[0] / steps
             cam_value = n_local / (cam_ms * 1e-3) / 1e6
 
+        # ---- informational: the SAM feature frame in the shape its consumer wants (nerf/trainer.py:540-546 resizes
+        # the [H,W,256] frame to [1,256,64,64] for the SAM decoder): host rays in, image + depth + weights_sum + the 64x64 NCHW
+        # feature tensor out -- the permute and the bilinear resize happen on the device, 4 MB instead of 655 MB cross PCIe
+        consumer_value = None
+        if wl == "sam" and world == 1 and not strong:
+            try:
+                small = {"image": torch.empty(n_local, 3).pin_memory(), "depth": torch.empty(n_local).pin_memory(),
+                         "weights_sum": torch.empty(n_local).pin_memory(), "samvit_nchw": torch.empty(1, 256, 64, 64).pin_memory()}
+
+                def step_consumer(i):
+                    ho, hd = host_rays[i % n_res]
+                    o_dev.copy_(ho, non_blocking=True)
+                    d_dev.copy_(hd, non_blocking=True)
+                    out = model.render(o_dev, d_dev, staged=False, perturb=False, return_feats=1, H=H, W=W, image_width=hint,
+                                       feature_layout="nchw", feature_size=(64, 64))
+                    for k, t in small.items():
+                        t.copy_(out[k], non_blocking=True)
+
+                consumer_ms = timed_loop(step_consumer, steps, warmup)[0] / steps
+                consumer_value = n_local / (consumer_ms * 1e-3) / 1e6
+            except Exception as e:   # noqa: BLE001 -- informational figure only
+                print(f"bench.py: consumer-shaped SAM frame not measured ({type(e).__name__}: {e})", file=sys.stderr)
+
         # pose-0 frame of this rank for the parity figure / checksum
         out0 = {k: v.clone() for k, v in render_frame(*dev_rays[0]).items()}
         torch.cuda.synchronize()
@@ -537,6 +560,7 @@ def measure(wl, args, ctx, H, W, headline, rows_of_rank=None, global_h=None, ste
             "e2e": {"value": e2e_value, "unit": "Mrays/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": 2 * n_local * 12 * world,
                     "d2h_bytes_per_step": int(sum(t.numel() * 4 for t in host_out.values())),
                     "d2h": "rank 0 reads every gathered output: " + ", ".join(keys), "render_image_uint8_value": cam_value,
+                    "sam_consumer_nchw64_value": consumer_value,
                     "streamed_value": stream_value, "streamed_ms_per_step": stream_ms,
                     "streamed": "same copies, on a copy stream: H2D of the next and D2H of the previous frame overlap the render"},
             "gpu_launches": int(launches),
